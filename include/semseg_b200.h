@@ -1,0 +1,194 @@
+/*
+ * semseg_b200 — C-ABI of the B200-native hot path of hszhao/semseg.
+ *
+ * Plain pointers and sizes only: no ATen / pybind types cross this boundary. Every entry point
+ * takes device pointers, a cudaStream_t passed as void*, returns 0 on success or a negative
+ * SEMSEG_E_* code, and never throws; semseg_last_error() returns the message of the last failure
+ * on the calling thread. All kernels are sm_100a-only; there is no CPU fallback behind this ABI.
+ *
+ * What each group replaces in the reference (paths relative to the hszhao/semseg tree):
+ *   - semseg_psamask_*        : lib/psa/src/gpu/operator.h:3-4 (psamask_forward_cuda / psamask_backward_cuda,
+ *                               kernels lib/psa/src/gpu/psamask_cuda.cu:8-128) bound by
+ *                               lib/psa/functions/psamask.py:19-35.
+ *   - semseg_conv_*           : the cuDNN convolutions behind nn.Conv2d at model/resnet.py:63-69,108-113,133-137
+ *                               (after the dilation patch model/pspnet.py:49-58), the heads
+ *                               model/pspnet.py:65-69,73-77 and PSA 1x1s model/psanet.py:24-51.
+ *   - semseg_bn_*             : nn.BatchNorm2d / nn.SyncBatchNorm (training + eval) and the in-place ReLU and
+ *                               residual add around them, model/resnet.py:77-92.
+ *   - semseg_pack_* / layout  : NCHW fp32 <-> NHWC bf16 at the module boundary (model/pspnet.py:80-105).
+ *   - semseg_ppm_* / pool     : model/pspnet.py:12-26 (AdaptiveAvgPool2d, bilinear upsample, concat),
+ *                               nn.MaxPool2d at model/resnet.py:115.
+ *   - semseg_upsample_ce_*    : F.interpolate + CrossEntropyLoss + argmax, model/pspnet.py:94-103.
+ *
+ * Activations are NHWC bf16 in HBM; "pitch" arguments are the distance between consecutive pixels in
+ * elements (>= channels; lets a kernel read/write a channel slice of a wider concat buffer).
+ */
+#ifndef SEMSEG_B200_H
+#define SEMSEG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEMSEG_OK 0
+#define SEMSEG_E_INVALID (-1)  /* bad argument (shape, alignment, null pointer) */
+#define SEMSEG_E_CUDA (-2)     /* CUDA runtime / driver error (message in semseg_last_error) */
+#define SEMSEG_E_UNSUPPORTED (-3)
+
+#define SEMSEG_MAX_TAPS 9
+
+const char* semseg_last_error(void);
+int semseg_abi_version(void);
+/* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
+long long semseg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * PSA mask (collect / distribute), fp32 NCHW exactly as the reference.
+ *   psa_type 0 = collect, 1 = distribute (lib/psa/functions/psamask.py:9).
+ *   fwd: in  [N, mH*mW, H, W] -> out [N, H*W, H, W]; every element of out is written (zeros included),
+ *        so the caller does NOT need to pre-zero it (the reference requires a zeroed buffer).
+ *   bwd: dout [N, H*W, H, W] -> din [N, mH*mW, H, W]; every element of din is written.
+ */
+int semseg_psamask_fwd(int psa_type, const float* in, float* out, int N, int H, int W, int mH, int mW,
+                       void* stream);
+int semseg_psamask_bwd(int psa_type, const float* dout, float* din, int N, int H, int W, int mH, int mW,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).
+ *
+ * One descriptor drives fprop and dgrad (dgrad = fprop of dY with the transposed/flipped packed
+ * weights). The output pixel grid is [N, H, W]; tap t reads input pixel
+ * (n*img_mul + img_add[t], h + dh[t], w + dw[t]) of an input tensor [Nin, Hin, Win, Cin] with zero fill
+ * outside it, multiplied by packed-weight slab wtap[t] of a [n_wtaps][Cout_rows][Cin_cols] bf16 tensor.
+ */
+enum {
+  SEMSEG_EPI_RAW = 0,    /* y = bf16(acc); optional per-tile BN partial statistics */
+  SEMSEG_EPI_AFFINE = 1, /* y = bf16(act(acc*scale[c] + shift[c] + residual)); scale/shift/residual optional */
+  SEMSEG_EPI_F32 = 2     /* out_f32[pixel*out_pitch + c] = acc + shift[c] (bias), c < Cout */
+};
+
+typedef struct semseg_conv_desc {
+  /* output pixel grid and GEMM sizes */
+  int32_t N, H, W;
+  int32_t Cin, Cout;
+  /* input tensor (bf16 NHWC) */
+  const void* x;
+  int32_t Nin, Hin, Win, x_pitch;
+  /* packed weights (bf16 [n_wtaps][w_rows][w_cols], w_cols contiguous) */
+  const void* w;
+  int32_t n_wtaps, w_rows, w_cols;
+  /* taps */
+  int32_t taps;
+  int32_t dh[SEMSEG_MAX_TAPS], dw[SEMSEG_MAX_TAPS], wtap[SEMSEG_MAX_TAPS];
+  int32_t img_mul, img_add[SEMSEG_MAX_TAPS];
+  /* epilogue */
+  int32_t epi_mode;
+  int32_t relu;
+  void* y; /* bf16 NHWC output (RAW / AFFINE) */
+  int32_t y_pitch;
+  const float* scale;   /* [Cout] or NULL */
+  const float* shift;   /* [Cout] or NULL (bias in F32 mode) */
+  const void* residual; /* bf16 NHWC [N,H,W,*] or NULL */
+  int32_t res_pitch;
+  float* out_f32; /* F32 mode output */
+  int32_t out_pitch;
+  /* RAW mode statistics: stats_partial [num_m_tiles][2][Cout] (sum, M2 about the tile mean),
+   * tile_count [num_m_tiles]; NULL to skip. num_m_tiles from semseg_conv_num_m_tiles(). */
+  float* stats_partial;
+  float* tile_count;
+} semseg_conv_desc;
+
+/* Number of pixel tiles the kernel will use for an [N,H,W] output grid (size of the stats buffers). */
+int semseg_conv_num_m_tiles(int N, int H, int W);
+int semseg_conv_fprop(const semseg_conv_desc* d, void* stream);
+
+/* wgrad: dw_partial[split][tap][co][ci] (fp32) = sum over the split's pixels of dy[p, co] * x[p + off(tap), ci].
+ * Returns the number of splits through *n_splits (query with dw_partial == NULL first; the buffer must hold
+ * n_splits*taps*Cout*Cin floats). */
+typedef struct semseg_wgrad_desc {
+  int32_t N, H, W;
+  int32_t Cin, Cout;
+  const void* x; /* bf16 NHWC [Nin,Hin,Win,*] */
+  int32_t Nin, Hin, Win, x_pitch;
+  const void* dy; /* bf16 NHWC [N,H,W,*] */
+  int32_t dy_pitch;
+  int32_t taps;
+  int32_t dh[SEMSEG_MAX_TAPS], dw[SEMSEG_MAX_TAPS];
+  int32_t img_mul, img_add[SEMSEG_MAX_TAPS];
+  float* dw_partial;
+  int32_t n_splits; /* in: 0 = let the library choose; out (via semseg_conv_wgrad_splits) */
+} semseg_wgrad_desc;
+
+int semseg_conv_wgrad_splits(const semseg_wgrad_desc* d);
+int semseg_conv_wgrad(const semseg_wgrad_desc* d, void* stream);
+/* dw_oihw[co][ci][tap] (+)= sum_s dw_partial[s][tap][co][ci]; accumulate != 0 adds to the existing values. */
+int semseg_wgrad_reduce(const float* dw_partial, int n_splits, int taps, int Cout, int Cin, float* dw_oihw,
+                        int accumulate, void* stream);
+
+/* Weight packing: fp32 OIHW [Cout][Cin][taps] ->
+ *   wf bf16 [taps][rows_f][cols_f]  (wf[t][co][ci], zero padded)   — fprop B operand
+ *   wd bf16 [taps][rows_d][cols_d]  (wd[t][ci][co], zero padded)   — dgrad B operand
+ * Either output may be NULL. */
+int semseg_pack_weights(const float* w_oihw, int Cout, int Cin, int taps, void* wf, int rows_f, int cols_f,
+                        void* wd, int rows_d, int cols_d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout conversion at the module boundary.
+ */
+int semseg_nchw_f32_to_nhwc_bf16(const float* in, void* out, int N, int C, int H, int W, int out_pitch,
+                                 void* stream);
+int semseg_nhwc_bf16_to_nchw_f32(const void* in, float* out, int N, int C, int H, int W, int in_pitch,
+                                 void* stream);
+int semseg_nhwc_f32_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W, int in_pitch,
+                                void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm (training statistics, apply, backward) on NHWC bf16 tensors, fp32 statistics.
+ */
+/* Merge per-tile partials (Chan) into per-channel (mean, M2, count): out_stats [3][C]. */
+int semseg_bn_merge_partials(const float* stats_partial, const float* tile_count, int num_tiles, int C,
+                             float* out_stats, void* stream);
+/* Per-channel statistics of an arbitrary NHWC bf16 tensor [M pixels][C] (used where the producer is not the
+ * conv kernel): out_stats [3][C] = (mean, M2, count). */
+int semseg_bn_stats(const void* x, int M, int C, int pitch, float* workspace, long long workspace_floats,
+                    float* out_stats, void* stream);
+/* Scratch floats the two-stage reductions (bn_stats, bn_bwd_reduce) need for an [M][C] tensor. */
+long long semseg_bn_workspace_floats(int M, int C);
+/* Merge R rank-stat blocks [R][3][C] (R = 1 without SyncBN) and finalise:
+ *   mean_invstd [2][C]; scale_shift [2][C] with scale = gamma*invstd, shift = beta - mean*scale;
+ *   running_mean/var updated in place (momentum, unbiased var) when non-NULL. */
+int semseg_bn_finalize(const float* rank_stats, int R, int C, const float* gamma, const float* beta, float eps,
+                       float momentum, float* running_mean, float* running_var, float* mean_invstd,
+                       float* scale_shift, void* stream);
+/* Eval-mode folding: scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
+int semseg_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, int C, float* scale_shift, void* stream);
+/* y = act(x*scale[c] + shift[c] + residual). */
+int semseg_bn_apply(const void* x, int x_pitch, const float* scale_shift, const void* residual, int res_pitch,
+                    void* y, int y_pitch, int M, int C, int relu, void* stream);
+/* Backward reduce: with dz = dy * (y > 0 if relu) and xhat = (x - mean)*invstd,
+ *   sums [2][C] = (sum dz, sum dz*xhat). y may be NULL when relu == 0. */
+int semseg_bn_bwd_reduce(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x, int x_pitch,
+                         const float* mean_invstd, int M, int C, int relu, float* workspace,
+                         long long workspace_floats, float* sums, void* stream);
+/* Backward apply: dx = gamma*invstd*(dz - sum_dz/count - xhat*sum_dzxhat/count) (bf16);
+ *   dres (optional) = dz (bf16); dgamma = sum_dzxhat, dbeta = sum_dz written to dgamma_dbeta [2][C].
+ *   count = total number of samples per channel across all ranks. */
+int semseg_bn_bwd_apply(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x, int x_pitch,
+                        const float* mean_invstd, const float* gamma, const float* sums, float count, int M,
+                        int C, int relu, void* dx, int dx_pitch, void* dres, int dres_pitch,
+                        float* dgamma_dbeta, void* stream);
+/* dz = dy * (y > 0); plain ReLU backward for tensors without BN in between. */
+int semseg_relu_bwd(const void* dy, int dy_pitch, const void* y, int y_pitch, void* dz, int dz_pitch, int M,
+                    int C, void* stream);
+/* out = a + b (bf16 NHWC, used to merge gradient branches). */
+int semseg_add_bf16(const void* a, int a_pitch, const void* b, int b_pitch, void* out, int out_pitch, int M,
+                    int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMSEG_B200_H */

@@ -1,0 +1,123 @@
+"""ctypes binding of libsemseg_b200.so (the C-ABI declared in include/semseg_b200.h).
+
+The product path has no CPU fallback: if the library is missing or an entry point fails, this module
+raises. Nothing under oracle/ is ever imported from here.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsemseg_b200.so")
+
+MAX_TAPS = 9
+EPI_RAW, EPI_AFFINE, EPI_F32 = 0, 1, 2
+
+c_int = ctypes.c_int
+c_i32 = ctypes.c_int32
+c_vp = ctypes.c_void_p
+c_f = ctypes.c_float
+c_ll = ctypes.c_longlong
+I9 = c_i32 * MAX_TAPS
+
+
+class ConvDesc(ctypes.Structure):
+    """struct semseg_conv_desc (include/semseg_b200.h)."""
+    _fields_ = [
+        ("N", c_i32), ("H", c_i32), ("W", c_i32),
+        ("Cin", c_i32), ("Cout", c_i32),
+        ("x", c_vp),
+        ("Nin", c_i32), ("Hin", c_i32), ("Win", c_i32), ("x_pitch", c_i32),
+        ("w", c_vp),
+        ("n_wtaps", c_i32), ("w_rows", c_i32), ("w_cols", c_i32),
+        ("taps", c_i32),
+        ("dh", I9), ("dw", I9), ("wtap", I9),
+        ("img_mul", c_i32), ("img_add", I9),
+        ("epi_mode", c_i32), ("relu", c_i32),
+        ("y", c_vp), ("y_pitch", c_i32),
+        ("scale", c_vp), ("shift", c_vp),
+        ("residual", c_vp), ("res_pitch", c_i32),
+        ("out_f32", c_vp), ("out_pitch", c_i32),
+        ("stats_partial", c_vp), ("tile_count", c_vp),
+    ]
+
+
+class WgradDesc(ctypes.Structure):
+    """struct semseg_wgrad_desc (include/semseg_b200.h)."""
+    _fields_ = [
+        ("N", c_i32), ("H", c_i32), ("W", c_i32),
+        ("Cin", c_i32), ("Cout", c_i32),
+        ("x", c_vp),
+        ("Nin", c_i32), ("Hin", c_i32), ("Win", c_i32), ("x_pitch", c_i32),
+        ("dy", c_vp), ("dy_pitch", c_i32),
+        ("taps", c_i32),
+        ("dh", I9), ("dw", I9),
+        ("img_mul", c_i32), ("img_add", I9),
+        ("dw_partial", c_vp),
+        ("n_splits", c_i32),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/semseg_b200.h declares
+# (tests/test_abi.py parses the header and checks both directions).
+SIGNATURES = {
+    "semseg_last_error": (ctypes.c_char_p, []),
+    "semseg_abi_version": (c_int, []),
+    "semseg_launch_count": (c_ll, []),
+    "semseg_psamask_fwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_psamask_bwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_conv_num_m_tiles": (c_int, [c_int, c_int, c_int]),
+    "semseg_conv_fprop": (c_int, [ctypes.POINTER(ConvDesc), c_vp]),
+    "semseg_conv_wgrad_splits": (c_int, [ctypes.POINTER(WgradDesc)]),
+    "semseg_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_vp]),
+    "semseg_wgrad_reduce": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "semseg_pack_weights": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp]),
+    "semseg_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_nhwc_f32_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_bn_merge_partials": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "semseg_bn_stats": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_ll, c_vp, c_vp]),
+    "semseg_bn_workspace_floats": (c_ll, [c_int, c_int]),
+    "semseg_bn_finalize": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "semseg_bn_fold_eval": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_vp, c_vp]),
+    "semseg_bn_apply": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_bn_bwd_reduce": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp, c_ll,
+                                     c_vp, c_vp]),
+    "semseg_bn_bwd_apply": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_f, c_int, c_int,
+                                    c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
+    "semseg_relu_bwd": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp]),
+    "semseg_add_bf16": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp]),
+}
+
+_lib = None
+
+
+class SemsegError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and attach signatures. Raises if it is missing: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SemsegError(
+            "libsemseg_b200.so is not built (%s). Run `python -m semseg_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU/PyTorch fallback for this path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header/library drift: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().semseg_last_error()
+        raise SemsegError("%s failed (%d): %s" % (what, status, msg.decode() if msg else "?"))
+
+
+def launch_count():
+    return int(load().semseg_launch_count())

@@ -1,0 +1,531 @@
+// BatchNorm (training statistics, apply, backward), ReLU and residual kernels on NHWC bf16 tensors.
+// All statistics are fp32; per-tile / per-chunk partials are merged with Chan's parallel-variance
+// formula in a fixed order, so results are run-to-run deterministic.
+// Mirrors nn.BatchNorm2d / nn.SyncBatchNorm + ReLU + residual add as used at model/resnet.py:77-92
+// (biased variance for normalisation, unbiased for running_var, eps 1e-5, momentum 0.1).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace sb {
+
+struct Moments {
+  float n, mean, m2;
+};
+__device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
+  if (b.n == 0.f) return a;
+  if (a.n == 0.f) return b;
+  Moments r;
+  r.n = a.n + b.n;
+  const float d = b.mean - a.mean;
+  r.mean = a.mean + d * (b.n / r.n);
+  r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// partials [T][2][C] (sum, M2 about the tile mean) + counts [T]  ->  out [3][C] (mean, M2, count)
+// block = 32 channels x 32 tile lanes.
+__global__ void bn_merge_partials_kernel(const float* __restrict__ part, const float* __restrict__ cnt, int T, int C,
+                                         float* __restrict__ out) {
+  __shared__ Moments sm[32][33];
+  const int cl = threadIdx.x & 31;
+  const int tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  Moments acc = {0.f, 0.f, 0.f};
+  if (c < C) {
+    for (int t = tl; t < T; t += 32) {
+      const float n = cnt[t];
+      if (n > 0.f) {
+        Moments m;
+        m.n = n;
+        m.mean = part[(static_cast<size_t>(t) * 2) * C + c] / n;
+        m.m2 = part[(static_cast<size_t>(t) * 2 + 1) * C + c];
+        acc = merge(acc, m);
+      }
+    }
+  }
+  sm[tl][cl] = acc;
+  __syncthreads();
+  if (tl == 0 && c < C) {
+    Moments r = sm[0][cl];
+    for (int i = 1; i < 32; ++i) r = merge(r, sm[i][cl]);
+    out[c] = r.mean;
+    out[C + c] = r.m2;
+    out[2 * C + c] = r.n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic per-chunk statistics of x [M][pitch] (bf16): chunk = rows_per_chunk pixels.
+// block = 8 channel-groups (8 ch each = 64 channels) x 32 pixel lanes; grid = (C/64 ceil, chunks).
+__global__ void bn_chunk_stats_kernel(const __nv_bfloat16* __restrict__ x, int M, int C, int pitch,
+                                      int rows_per_chunk, float* __restrict__ part, float* __restrict__ cnt) {
+  __shared__ float s_sum[32][65];
+  const int gl = threadIdx.x & 7;   // channel group within block
+  const int pl = threadIdx.x >> 3;  // pixel lane 0..31
+  const int c0 = blockIdx.x * 64 + gl * 8;
+  const int chunk = blockIdx.y;
+  const int r0 = chunk * rows_per_chunk;
+  const int r1 = min(M, r0 + rows_per_chunk);
+  const bool active = c0 < C;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    for (int r = r0 + pl; r < r1; r += 32) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * pitch + c0);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        s[2 * q] += f.x;
+        s[2 * q + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s_sum[pl][gl * 8 + q] = s[q];
+  __syncthreads();
+  const float n = static_cast<float>(r1 - r0);
+  float mean[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += s_sum[i][gl * 8 + q];
+    mean[q] = t / n;
+    s[q] = t;  // total sum
+  }
+  __syncthreads();
+  float m2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    for (int r = r0 + pl; r < r1; r += 32) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * pitch + c0);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        const float d0 = f.x - mean[2 * q], d1 = f.y - mean[2 * q + 1];
+        m2[2 * q] = fmaf(d0, d0, m2[2 * q]);
+        m2[2 * q + 1] = fmaf(d1, d1, m2[2 * q + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s_sum[pl][gl * 8 + q] = m2[q];
+  __syncthreads();
+  if (pl == 0 && active) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float t = 0.f;
+      for (int i = 0; i < 32; ++i) t += s_sum[i][gl * 8 + q];
+      if (c0 + q < C) {
+        part[(static_cast<size_t>(chunk) * 2) * C + c0 + q] = s[q];
+        part[(static_cast<size_t>(chunk) * 2 + 1) * C + c0 + q] = t;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) cnt[chunk] = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rank_stats [R][3][C] -> mean_invstd [2][C], scale_shift [2][C], running stats update.
+__global__ void bn_finalize_kernel(const float* __restrict__ rs, int R, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_invstd, float* __restrict__ scale_shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  Moments acc = {0.f, 0.f, 0.f};
+  for (int r = 0; r < R; ++r) {
+    const float* b = rs + static_cast<size_t>(r) * 3 * C;
+    Moments m;
+    m.mean = b[c];
+    m.m2 = b[C + c];
+    m.n = b[2 * C + c];
+    acc = merge(acc, m);
+  }
+  const float var = acc.n > 0.f ? acc.m2 / acc.n : 0.f;
+  const float invstd = rsqrtf(var + eps);
+  mean_invstd[c] = acc.mean;
+  mean_invstd[C + c] = invstd;
+  const float g = gamma ? gamma[c] : 1.f;
+  const float bt = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = bt - acc.mean * sc;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * acc.mean;
+  if (running_var) {
+    const float unb = acc.n > 1.f ? acc.m2 / (acc.n - 1.f) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+  }
+}
+
+__global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
+                                    float* __restrict__ scale_shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = rsqrtf(rv[c] + eps);
+  const float sc = (gamma ? gamma[c] : 1.f) * invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = (beta ? beta[c] : 0.f) - rm[c] * sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 t = __bfloat1622float2(h[q]);
+    f[2 * q] = t.x;
+    f[2 * q + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, const float* __restrict__ ss,
+                                const __nv_bfloat16* __restrict__ res, int res_pitch, __nv_bfloat16* __restrict__ y,
+                                int y_pitch, long long M, int C, int relu) {
+  const int groups = C >> 3;
+  const long long total = M * groups;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = idx / groups;
+    const int c0 = static_cast<int>(idx - p * groups) << 3;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), f);
+    const float4 s0 = *reinterpret_cast<const float4*>(ss + c0), s1 = *reinterpret_cast<const float4*>(ss + c0 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(ss + C + c0),
+                 h1 = *reinterpret_cast<const float4*>(ss + C + c0 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (res) unpack8(*reinterpret_cast<const uint4*>(res + p * res_pitch + c0), r);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float v = fmaf(f[q], sc[q], sh[q]) + r[q];
+      if (relu) v = fmaxf(v, 0.f);
+      f[q] = v;
+    }
+    *reinterpret_cast<uint4*>(y + p * y_pitch + c0) = pack8(f);
+  }
+}
+
+// Backward reduce, stage 1: per-chunk sums of dz and dz*xhat. block = 8 groups x 32 pixel lanes.
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pitch,
+                                     const __nv_bfloat16* __restrict__ y, int y_pitch,
+                                     const __nv_bfloat16* __restrict__ x, int x_pitch,
+                                     const float* __restrict__ mean_invstd, int M, int C, int relu,
+                                     int rows_per_chunk, float* __restrict__ part) {
+  __shared__ float s_a[32][65];
+  __shared__ float s_b[32][65];
+  const int gl = threadIdx.x & 7;
+  const int pl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + gl * 8;
+  const int chunk = blockIdx.y;
+  const int r0 = chunk * rows_per_chunk;
+  const int r1 = min(M, r0 + rows_per_chunk);
+  const bool active = c0 < C;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    float mean[8], invstd[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      mean[q] = mean_invstd[c0 + q];
+      invstd[q] = mean_invstd[C + c0 + q];
+    }
+    for (int r = r0 + pl; r < r1; r += 32) {
+      float d[8], xv[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * dy_pitch + c0), d);
+      unpack8(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * x_pitch + c0), xv);
+      if (relu) {
+        float yv[8];
+        unpack8(*reinterpret_cast<const uint4*>(y + static_cast<size_t>(r) * y_pitch + c0), yv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (!(yv[q] > 0.f)) d[q] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        a[q] += d[q];
+        b[q] = fmaf(d[q], (xv[q] - mean[q]) * invstd[q], b[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    s_a[pl][gl * 8 + q] = a[q];
+    s_b[pl][gl * 8 + q] = b[q];
+  }
+  __syncthreads();
+  if (pl < 2 && active) {
+    // pl 0 reduces the dz sums, pl 1 the dz*xhat sums
+    float(*src)[65] = pl == 0 ? s_a : s_b;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float t = 0.f;
+      for (int i = 0; i < 32; ++i) t += src[i][gl * 8 + q];
+      if (c0 + q < C) part[(static_cast<size_t>(chunk) * 2 + pl) * C + c0 + q] = t;
+    }
+  }
+}
+
+// stage 2: sums[2][C] = sum over chunks (fixed order).
+__global__ void bn_bwd_reduce_final_kernel(const float* __restrict__ part, int chunks, int C,
+                                           float* __restrict__ sums) {
+  __shared__ float sm[32][33];
+  const int cl = threadIdx.x & 31;
+  const int tl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + cl;  // over 2*C: [which][c]
+  float acc = 0.f;
+  if (idx < 2 * C) {
+    const int which = idx / C, c = idx - which * C;
+    for (int t = tl; t < chunks; t += 32) acc += part[(static_cast<size_t>(t) * 2 + which) * C + c];
+  }
+  sm[tl][cl] = acc;
+  __syncthreads();
+  if (tl == 0 && idx < 2 * C) {
+    float r = 0.f;
+    for (int i = 0; i < 32; ++i) r += sm[i][cl];
+    sums[idx] = r;
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pitch,
+                                    const __nv_bfloat16* __restrict__ y, int y_pitch,
+                                    const __nv_bfloat16* __restrict__ x, int x_pitch,
+                                    const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ sums, float inv_count, long long M, int C, int relu,
+                                    __nv_bfloat16* __restrict__ dx, int dx_pitch, __nv_bfloat16* __restrict__ dres,
+                                    int dres_pitch, float* __restrict__ dgamma_dbeta) {
+  const int groups = C >> 3;
+  const long long total = M * groups;
+  if (dgamma_dbeta && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dgamma_dbeta[c] = sums[C + c];
+      dgamma_dbeta[C + c] = sums[c];
+    }
+  }
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = idx / groups;
+    const int c0 = static_cast<int>(idx - p * groups) << 3;
+    float d[8], xv[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + p * dy_pitch + c0), d);
+    unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), xv);
+    if (relu) {
+      float yv[8];
+      unpack8(*reinterpret_cast<const uint4*>(y + p * y_pitch + c0), yv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (!(yv[q] > 0.f)) d[q] = 0.f;
+    }
+    if (dres) *reinterpret_cast<uint4*>(dres + p * dres_pitch + c0) = pack8(d);
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = c0 + q;
+      const float mean = mean_invstd[c], invstd = mean_invstd[C + c];
+      const float g = gamma ? gamma[c] : 1.f;
+      const float xhat = (xv[q] - mean) * invstd;
+      o[q] = g * invstd * (d[q] - sums[c] * inv_count - xhat * sums[C + c] * inv_count);
+    }
+    *reinterpret_cast<uint4*>(dx + p * dx_pitch + c0) = pack8(o);
+  }
+}
+
+__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pitch,
+                                const __nv_bfloat16* __restrict__ y, int y_pitch, __nv_bfloat16* __restrict__ dz,
+                                int dz_pitch, long long M, int C) {
+  const int groups = C >> 3;
+  const long long total = M * groups;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = idx / groups;
+    const int c0 = static_cast<int>(idx - p * groups) << 3;
+    float d[8], yv[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + p * dy_pitch + c0), d);
+    unpack8(*reinterpret_cast<const uint4*>(y + p * y_pitch + c0), yv);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (!(yv[q] > 0.f)) d[q] = 0.f;
+    *reinterpret_cast<uint4*>(dz + p * dz_pitch + c0) = pack8(d);
+  }
+}
+
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, int a_pitch, const __nv_bfloat16* __restrict__ b,
+                                int b_pitch, __nv_bfloat16* __restrict__ out, int out_pitch, long long M, int C) {
+  const int groups = C >> 3;
+  const long long total = M * groups;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = idx / groups;
+    const int c0 = static_cast<int>(idx - p * groups) << 3;
+    float x[8], z[8];
+    unpack8(*reinterpret_cast<const uint4*>(a + p * a_pitch + c0), x);
+    unpack8(*reinterpret_cast<const uint4*>(b + p * b_pitch + c0), z);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] += z[q];
+    *reinterpret_cast<uint4*>(out + p * out_pitch + c0) = pack8(x);
+  }
+}
+
+static int ew_grid(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+static int chunk_rows(int M) {
+  int rows = cdiv(M, 1024);
+  if (rows < 256) rows = 256;
+  return (rows + 31) & ~31;
+}
+
+}  // namespace sb
+
+using namespace sb;
+typedef __nv_bfloat16 bf16;
+
+extern "C" long long semseg_bn_workspace_floats(int M, int C) {
+  if (M <= 0 || C <= 0) return 0;
+  const int rows = chunk_rows(M);
+  const long long chunks = cdiv(M, rows);
+  return chunks * 2 * C + chunks + 3LL * C;
+}
+
+extern "C" int semseg_bn_merge_partials(const float* stats_partial, const float* tile_count, int num_tiles, int C,
+                                        float* out_stats, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(stats_partial && tile_count && out_stats && num_tiles > 0 && C > 0, "bn_merge_partials: bad args");
+  bn_merge_partials_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, tile_count, num_tiles, C, out_stats);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_bn_stats(const void* x, int M, int C, int pitch, float* workspace, long long workspace_floats,
+                               float* out_stats, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(x && workspace && out_stats && M > 0 && C > 0, "bn_stats: bad args");
+  SB_CHECK_ARG(C % 8 == 0 && pitch % 8 == 0 && pitch >= C, "bn_stats: C/pitch must be multiples of 8");
+  SB_CHECK_ARG(workspace_floats >= semseg_bn_workspace_floats(M, C), "bn_stats: workspace too small");
+  const int rows = chunk_rows(M);
+  const int chunks = cdiv(M, rows);
+  float* part = workspace;
+  float* cnt = workspace + static_cast<size_t>(chunks) * 2 * C;
+  dim3 grid(cdiv(C, 64), chunks);
+  bn_chunk_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), M, C, pitch, rows, part, cnt);
+  SB_LAUNCHED();
+  bn_merge_partials_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(part, cnt, chunks, C, out_stats);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_bn_finalize(const float* rank_stats, int R, int C, const float* gamma, const float* beta,
+                                  float eps, float momentum, float* running_mean, float* running_var,
+                                  float* mean_invstd, float* scale_shift, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(rank_stats && mean_invstd && scale_shift && R > 0 && C > 0, "bn_finalize: bad args");
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, stream>>>(rank_stats, R, C, gamma, beta, eps, momentum, running_mean,
+                                                      running_var, mean_invstd, scale_shift);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
+                                   const float* running_var, float eps, int C, float* scale_shift, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(running_mean && running_var && scale_shift && C > 0, "bn_fold_eval: bad args");
+  bn_fold_eval_kernel<<<cdiv(C, 128), 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, C, scale_shift);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_bn_apply(const void* x, int x_pitch, const float* scale_shift, const void* residual,
+                               int res_pitch, void* y, int y_pitch, int M, int C, int relu, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(x && scale_shift && y && M > 0 && C > 0, "bn_apply: bad args");
+  SB_CHECK_ARG(C % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && (!residual || res_pitch % 8 == 0),
+               "bn_apply: channels and pitches must be multiples of 8");
+  const long long total = static_cast<long long>(M) * (C / 8);
+  bn_apply_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_pitch, scale_shift,
+                                                           static_cast<const bf16*>(residual), res_pitch,
+                                                           static_cast<bf16*>(y), y_pitch, M, C, relu);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_bn_bwd_reduce(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x,
+                                    int x_pitch, const float* mean_invstd, int M, int C, int relu, float* workspace,
+                                    long long workspace_floats, float* sums, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(dy && x && mean_invstd && workspace && sums && M > 0 && C > 0, "bn_bwd_reduce: bad args");
+  SB_CHECK_ARG(!relu || y, "bn_bwd_reduce: relu needs y");
+  SB_CHECK_ARG(C % 8 == 0 && dy_pitch % 8 == 0 && x_pitch % 8 == 0 && (!relu || y_pitch % 8 == 0),
+               "bn_bwd_reduce: channels and pitches must be multiples of 8");
+  SB_CHECK_ARG(workspace_floats >= semseg_bn_workspace_floats(M, C), "bn_bwd_reduce: workspace too small");
+  const int rows = chunk_rows(M);
+  const int chunks = cdiv(M, rows);
+  dim3 grid(cdiv(C, 64), chunks);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_pitch, static_cast<const bf16*>(y),
+                                                 y_pitch, static_cast<const bf16*>(x), x_pitch, mean_invstd, M, C,
+                                                 relu, rows, workspace);
+  SB_LAUNCHED();
+  bn_bwd_reduce_final_kernel<<<cdiv(2 * C, 32), 1024, 0, stream>>>(workspace, chunks, C, sums);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_bn_bwd_apply(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x,
+                                   int x_pitch, const float* mean_invstd, const float* gamma, const float* sums,
+                                   float count, int M, int C, int relu, void* dx, int dx_pitch, void* dres,
+                                   int dres_pitch, float* dgamma_dbeta, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(dy && x && mean_invstd && sums && dx && M > 0 && C > 0 && count > 0.f, "bn_bwd_apply: bad args");
+  SB_CHECK_ARG(!relu || y, "bn_bwd_apply: relu needs y");
+  SB_CHECK_ARG(C % 8 == 0 && dy_pitch % 8 == 0 && x_pitch % 8 == 0 && dx_pitch % 8 == 0 &&
+                   (!relu || y_pitch % 8 == 0) && (!dres || dres_pitch % 8 == 0),
+               "bn_bwd_apply: channels and pitches must be multiples of 8");
+  const long long total = static_cast<long long>(M) * (C / 8);
+  bn_bwd_apply_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(
+      static_cast<const bf16*>(dy), dy_pitch, static_cast<const bf16*>(y), y_pitch, static_cast<const bf16*>(x),
+      x_pitch, mean_invstd, gamma, sums, 1.f / count, M, C, relu, static_cast<bf16*>(dx), dx_pitch,
+      static_cast<bf16*>(dres), dres_pitch, dgamma_dbeta);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_relu_bwd(const void* dy, int dy_pitch, const void* y, int y_pitch, void* dz, int dz_pitch,
+                               int M, int C, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(dy && y && dz && M > 0 && C > 0 && C % 8 == 0 && dy_pitch % 8 == 0 && y_pitch % 8 == 0 &&
+                   dz_pitch % 8 == 0,
+               "relu_bwd: bad args");
+  const long long total = static_cast<long long>(M) * (C / 8);
+  relu_bwd_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_pitch,
+                                                           static_cast<const bf16*>(y), y_pitch,
+                                                           static_cast<bf16*>(dz), dz_pitch, M, C);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_add_bf16(const void* a, int a_pitch, const void* b, int b_pitch, void* out, int out_pitch,
+                               int M, int C, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(a && b && out && M > 0 && C > 0 && C % 8 == 0 && a_pitch % 8 == 0 && b_pitch % 8 == 0 &&
+                   out_pitch % 8 == 0,
+               "add_bf16: bad args");
+  const long long total = static_cast<long long>(M) * (C / 8);
+  add_bf16_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(a), a_pitch,
+                                                           static_cast<const bf16*>(b), b_pitch,
+                                                           static_cast<bf16*>(out), out_pitch, M, C);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}

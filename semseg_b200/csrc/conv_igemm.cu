@@ -1,0 +1,456 @@
+// Implicit-GEMM convolution (fprop and dgrad) for NHWC bf16 activations on tcgen05 tensor cores.
+//
+//   out[p, co] = sum_t sum_ci x[p + off(t), ci] * w[t][co][ci]
+//
+// GEMM view: M = pixels (tiles of a bh x bw pixel rectangle inside one image, <= 128 rows),
+// N = Cout (BLOCK_N columns per tile), K = taps * Cin in blocks of 64 channels.
+//
+// Replaces the cuDNN convolutions behind nn.Conv2d in the reference (model/resnet.py:63-69,
+// model/pspnet.py:49-58,65-69,73-77). One persistent CTA per SM, warp-specialised:
+//   warp 0   : TMA producer   — A tile = 4-D box [64 ch, bw, bh, 1] at the tap-shifted pixel
+//                               (TMA zero-fills the halo), B tile = 3-D box [64, BLOCK_N, 1] of the
+//                               packed weights; both land in 128B-swizzled shared memory.
+//   warp 1   : MMA issuer     — one elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16),
+//                               accumulators live in TMEM (2 stages so the epilogue overlaps the next tile).
+//   warps 2-5: epilogue       — tcgen05.ld -> registers -> (affine / ReLU / residual) -> bf16 ->
+//                               swizzled smem -> TMA store; per-tile BatchNorm partial statistics
+//                               (sum, M2 about the tile mean) of the stored bf16 values.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace sb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle span
+constexpr int kNumThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kStageOutBytes = kBlockM * 64 * 2;    // 16 KB epilogue staging chunk (64 columns)
+constexpr int kMiscBytes = 2048;
+
+template <int BLOCK_N>
+struct ConvCfg {
+  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStageOutBytes + kMiscBytes + 1024;
+};
+
+struct ConvKParams {
+  int N, H, W;
+  int Cin, Cout;
+  int taps;
+  int bh, bw, tiles_h, tiles_w;
+  int n_tiles, num_m_tiles;
+  int k_chunks;  // ceil(Cin / 64)
+  int dh[SEMSEG_MAX_TAPS], dw[SEMSEG_MAX_TAPS], wtap[SEMSEG_MAX_TAPS], img_add[SEMSEG_MAX_TAPS];
+  int img_mul;
+  int epi_mode, relu;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  int res_pitch;
+  float* out_f32;
+  int out_pitch;
+  float* stats_partial;
+  float* tile_count;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const ConvKParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* out_stage = smem + kStages * Cfg::kStageBytes;  // 2 x 16 KB
+  uint8_t* misc = out_stage + 2 * kStageOutBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint32_t* row_mask = tmem_ptr + 1;                                // [4] valid-row bits per 32-row group
+  float* stat_scratch = reinterpret_cast<float*>(misc + 512);       // [2 halves][64 cols][3]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.n_tiles;
+  const int num_kb = p.taps * p.k_chunks;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.bh * p.bw) * 128u;
+  const uint32_t stage_tx = a_bytes + static_cast<uint32_t>(Cfg::kBTileBytes);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int tiles_per_img = p.tiles_h * p.tiles_w;
+        const int img = m_tile / tiles_per_img;
+        const int rem = m_tile - img * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.bh;
+        const int w0 = (rem % p.tiles_w) * p.bw;
+        const int n0 = n_tile * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t par = (it / kStages) & 1;
+          mbar_wait(&empty_bar[s], par ^ 1);
+          const int cb = kb / p.taps;
+          const int t = kb - cb * p.taps;
+          uint8_t* a_dst = stage_base + s * Cfg::kStageBytes;
+          uint8_t* b_dst = a_dst + kATileBytes;
+          mbar_expect_tx(&full_bar[s], stage_tx);
+          tma_load_4d(a_dst, &tmA, &full_bar[s], cb * kBlockK, w0 + p.dw[t], h0 + p.dh[t],
+                      img * p.img_mul + p.img_add[t]);
+          // 3-D weights [taps][rows][cols]: coordinates (k, row, tap)
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+              "%5}], [%2];" ::"r"(smem_u32(b_dst)),
+              "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[s])), "r"(cb * kBlockK), "r"(n0),
+              "r"(p.wtap[t])
+              : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int it = 0;
+      int tile_iter = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+        const int as = tile_iter & 1;
+        const uint32_t apar = (tile_iter >> 1) & 1;
+        mbar_wait(&tmem_empty[as], apar ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t par = (it / kStages) & 1;
+          mbar_wait(&full_bar[s], par);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(stage_base + s * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + kATileBytes;
+          const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle span
+            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&tmem_full[as]);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int g = warp & 3;             // TMEM lane group this warp may access
+    const int row = g * 32 + lane;      // accumulator row == pixel within the tile
+    const int et = (warp - 2) * 32 + lane;  // 0..127
+    const int scol = et & 63;           // statistics: column within the 64-wide chunk
+    const int shalf = et >> 6;          // statistics: which 64-row half
+    int tile_iter = 0;
+    int store_buf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int tiles_per_img = p.tiles_h * p.tiles_w;
+      const int img = m_tile / tiles_per_img;
+      const int rem = m_tile - img * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * p.bh;
+      const int w0 = (rem % p.tiles_w) * p.bw;
+      const int n0 = n_tile * BLOCK_N;
+      const int hi = row / p.bw;
+      const int wi = row - hi * p.bw;
+      const bool row_valid = (row < p.bh * p.bw) && (h0 + hi < p.H) && (w0 + wi < p.W);
+      const long long pix = (static_cast<long long>(img) * p.H + (h0 + hi)) * p.W + (w0 + wi);
+      {
+        const uint32_t m = __ballot_sync(0xffffffffu, row_valid);
+        if (lane == 0) row_mask[g] = m;
+      }
+      const int as = tile_iter & 1;
+      const uint32_t apar = (tile_iter >> 1) & 1;
+      mbar_wait(&tmem_full[as], apar);
+      tc_fence_after();
+
+      constexpr int kChunks = BLOCK_N / 64;
+#pragma unroll 1
+      for (int ch = 0; ch < kChunks; ++ch) {
+        const int c0 = n0 + ch * 64;  // first output channel of this chunk
+        if (c0 >= p.Cout) break;      // (uniform) nothing to write for padded columns
+        uint32_t v[2][32];
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(g * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N + ch * 64);
+        tmem_ld_32x32(taddr, v[0]);
+        tmem_ld_32x32(taddr + 32, v[1]);
+        tmem_ld_wait();
+
+        if (p.epi_mode == SEMSEG_EPI_F32) {
+          if (row_valid) {
+            float* orow = p.out_f32 + pix * p.out_pitch;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              const int c = c0 + j;
+              if (c < p.Cout) {
+                float a = __uint_as_float(v[j >> 5][j & 31]);
+                if (p.shift) a += __ldg(p.shift + c);
+                orow[c] = a;
+              }
+            }
+          }
+          continue;
+        }
+
+        if (p.epi_mode == SEMSEG_EPI_AFFINE) {
+          const __nv_bfloat16* rrow = (p.residual && row_valid) ? p.residual + pix * p.res_pitch + c0 : nullptr;
+#pragma unroll
+          for (int j8 = 0; j8 < 8; ++j8) {
+            float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (rrow) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + j8 * 8);
+              const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __bfloat1622float2(rp[q]);
+                r[2 * q] = f.x;
+                r[2 * q + 1] = f.y;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int j = j8 * 8 + q;
+              const int c = c0 + j;
+              float a = __uint_as_float(v[j >> 5][j & 31]);
+              const float sc = p.scale ? __ldg(p.scale + c) : 1.f;
+              const float sh = p.shift ? __ldg(p.shift + c) : 0.f;
+              a = fmaf(a, sc, sh) + r[q];
+              if (p.relu) a = fmaxf(a, 0.f);
+              v[j >> 5][j & 31] = __float_as_uint(a);
+            }
+          }
+        }
+
+        // registers -> bf16 -> 128B-swizzled staging tile (row = pixel, 64 channels = 128 bytes)
+        uint8_t* obuf = out_stage + store_buf * kStageOutBytes;
+        if (et == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained
+        named_bar_sync(1, kEpiThreads);
+#pragma unroll
+        for (int j8 = 0; j8 < 8; ++j8) {
+          uint4 o;
+          const int b = j8 * 8;
+          o.x = pack_bf16x2(__uint_as_float(v[b >> 5][(b + 0) & 31]), __uint_as_float(v[b >> 5][(b + 1) & 31]));
+          o.y = pack_bf16x2(__uint_as_float(v[b >> 5][(b + 2) & 31]), __uint_as_float(v[b >> 5][(b + 3) & 31]));
+          o.z = pack_bf16x2(__uint_as_float(v[b >> 5][(b + 4) & 31]), __uint_as_float(v[b >> 5][(b + 5) & 31]));
+          o.w = pack_bf16x2(__uint_as_float(v[b >> 5][(b + 6) & 31]), __uint_as_float(v[b >> 5][(b + 7) & 31]));
+          *reinterpret_cast<uint4*>(obuf + row * 128 + ((j8 ^ (row & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, kEpiThreads);
+        if (et == 0) {
+          tma_store_4d(&tmC, obuf, c0, w0, h0, img);
+          tma_store_commit();
+        }
+
+        if (p.stats_partial != nullptr && p.epi_mode == SEMSEG_EPI_RAW) {
+          // Per-column statistics of the bf16 values just staged (what BN-apply will read back).
+          // Each thread: one column, 64 rows; the two halves are merged with Chan's formula.
+          const int rbase = shalf * 64;
+          const uint32_t m_lo = row_mask[shalf * 2], m_hi = row_mask[shalf * 2 + 1];
+          float s = 0.f;
+          int cnt = 0;
+          const uint8_t* colp = obuf + (scol & 7) * 2;
+          const int chunk16 = scol >> 3;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            const uint32_t bit = (r < 32) ? ((m_lo >> r) & 1u) : ((m_hi >> (r - 32)) & 1u);
+            const int rr = rbase + r;
+            const float x = __bfloat162float(
+                *reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + ((chunk16 ^ (rr & 7)) << 4)));
+            if (bit) {
+              s += x;
+              ++cnt;
+            }
+          }
+          const float mean_h = cnt > 0 ? s / static_cast<float>(cnt) : 0.f;
+          float m2 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            const uint32_t bit = (r < 32) ? ((m_lo >> r) & 1u) : ((m_hi >> (r - 32)) & 1u);
+            const int rr = rbase + r;
+            const float x = __bfloat162float(
+                *reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + ((chunk16 ^ (rr & 7)) << 4)));
+            if (bit) {
+              const float d = x - mean_h;
+              m2 = fmaf(d, d, m2);
+            }
+          }
+          float* sc = stat_scratch + (shalf * 64 + scol) * 3;
+          sc[0] = s;
+          sc[1] = m2;
+          sc[2] = static_cast<float>(cnt);
+          named_bar_sync(2, kEpiThreads);
+          if (shalf == 0) {
+            const float* o = stat_scratch + (64 + scol) * 3;
+            const float s1 = o[0], m21 = o[1], n1 = o[2];
+            const float n0f = static_cast<float>(cnt);
+            const float nt = n0f + n1;
+            float tot_m2 = m2 + m21;
+            if (n0f > 0.f && n1 > 0.f) {
+              const float dlt = s1 / n1 - mean_h;
+              tot_m2 += dlt * dlt * n0f * n1 / nt;
+            }
+            float* dst = p.stats_partial + static_cast<size_t>(m_tile) * 2 * p.Cout;
+            dst[c0 + scol] = s + s1;
+            dst[p.Cout + c0 + scol] = tot_m2;
+            if (n_tile == 0 && ch == 0 && scol == 0 && p.tile_count) p.tile_count[m_tile] = nt;
+          }
+          named_bar_sync(2, kEpiThreads);  // scratch may be rewritten by the next chunk
+        }
+        store_buf ^= 1;
+      }
+      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvKParams& kp,
+                       cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int num_tiles = kp.num_m_tiles * kp.n_tiles;
+  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  conv_igemm_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, kp);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+}  // namespace sb
+
+extern "C" int semseg_conv_num_m_tiles(int N, int H, int W) {
+  int bh, bw;
+  sb::choose_box(H, W, sb::kBlockM, &bh, &bw);
+  return N * sb::cdiv(H, bh) * sb::cdiv(W, bw);
+}
+
+extern "C" int semseg_conv_fprop(const semseg_conv_desc* d, void* stream_) {
+  using namespace sb;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(d != nullptr, "conv: null descriptor");
+  SB_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: bad sizes");
+  SB_CHECK_ARG(d->taps >= 1 && d->taps <= SEMSEG_MAX_TAPS, "conv: taps=%d out of range", d->taps);
+  SB_CHECK_ARG(d->x && d->w, "conv: null x/w");
+  SB_CHECK_ARG(d->x_pitch % 8 == 0 && d->x_pitch >= d->Cin, "conv: x_pitch %d must be a multiple of 8 and >= Cin",
+               d->x_pitch);
+  SB_CHECK_ARG(d->w_cols % 8 == 0 && d->w_cols >= d->Cin, "conv: w_cols %d must be a multiple of 8 and >= Cin",
+               d->w_cols);
+  SB_CHECK_ARG(d->epi_mode >= 0 && d->epi_mode <= 2, "conv: bad epi_mode");
+
+  ConvKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.N = d->N; kp.H = d->H; kp.W = d->W; kp.Cin = d->Cin; kp.Cout = d->Cout; kp.taps = d->taps;
+  choose_box(d->H, d->W, kBlockM, &kp.bh, &kp.bw);
+  kp.tiles_h = cdiv(d->H, kp.bh);
+  kp.tiles_w = cdiv(d->W, kp.bw);
+  kp.num_m_tiles = d->N * kp.tiles_h * kp.tiles_w;
+  kp.k_chunks = cdiv(d->Cin, kBlockK);
+  for (int t = 0; t < d->taps; ++t) {
+    kp.dh[t] = d->dh[t]; kp.dw[t] = d->dw[t]; kp.wtap[t] = d->wtap[t]; kp.img_add[t] = d->img_add[t];
+    SB_CHECK_ARG(d->wtap[t] >= 0 && d->wtap[t] < d->n_wtaps, "conv: wtap[%d]=%d out of range", t, d->wtap[t]);
+  }
+  kp.img_mul = d->img_mul;
+  kp.epi_mode = d->epi_mode; kp.relu = d->relu;
+  kp.scale = d->scale; kp.shift = d->shift;
+  kp.residual = static_cast<const __nv_bfloat16*>(d->residual); kp.res_pitch = d->res_pitch;
+  kp.out_f32 = d->out_f32; kp.out_pitch = d->out_pitch;
+  kp.stats_partial = d->stats_partial; kp.tile_count = d->tile_count;
+
+  int block_n;
+  if (d->Cout % 256 == 0 || d->Cout > 128) block_n = 256;
+  else if (d->Cout > 64) block_n = 128;
+  else block_n = 64;
+  kp.n_tiles = cdiv(d->Cout, block_n);
+
+  // A: input activations [Nin][Hin][Win][x_pitch] viewed as (C, W, H, N)
+  CUtensorMap tmA, tmB, tmC;
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->Nin};
+    uint64_t str[3] = {(uint64_t)d->x_pitch * 2, (uint64_t)d->x_pitch * 2 * d->Win,
+                       (uint64_t)d->x_pitch * 2 * d->Win * d->Hin};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)kp.bw, (uint32_t)kp.bh, 1};
+    int r = encode_tmap_bf16(&tmA, d->x, 4, dims, str, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->w_cols, (uint64_t)d->w_rows, (uint64_t)d->n_wtaps};
+    uint64_t str[2] = {(uint64_t)d->w_cols * 2, (uint64_t)d->w_cols * 2 * d->w_rows};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)block_n, 1};
+    int r = encode_tmap_bf16(&tmB, d->w, 3, dims, str, box);
+    if (r) return r;
+  }
+  if (d->epi_mode == SEMSEG_EPI_F32) {
+    SB_CHECK_ARG(d->out_f32 != nullptr && d->out_pitch >= d->Cout, "conv: F32 epilogue needs out_f32/out_pitch");
+    tmC = tmA;  // unused
+  } else {
+    SB_CHECK_ARG(d->y != nullptr, "conv: null y");
+    SB_CHECK_ARG(d->Cout % 64 == 0, "conv: bf16 epilogue needs Cout %% 64 == 0 (got %d)", d->Cout);
+    SB_CHECK_ARG(d->y_pitch % 8 == 0 && d->y_pitch >= d->Cout, "conv: bad y_pitch %d", d->y_pitch);
+    if (d->residual) SB_CHECK_ARG(d->res_pitch % 8 == 0, "conv: res_pitch must be a multiple of 8");
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)d->y_pitch * 2, (uint64_t)d->y_pitch * 2 * d->W,
+                       (uint64_t)d->y_pitch * 2 * d->W * d->H};
+    uint32_t box[4] = {64u, (uint32_t)kp.bw, (uint32_t)kp.bh, 1};
+    int r = encode_tmap_bf16(&tmC, d->y, 4, dims, str, box);
+    if (r) return r;
+  }
+  switch (block_n) {
+    case 256: return launch_conv<256>(tmA, tmB, tmC, kp, stream);
+    case 128: return launch_conv<128>(tmA, tmB, tmC, kp, stream);
+    default: return launch_conv<64>(tmA, tmB, tmC, kp, stream);
+  }
+}

@@ -1,0 +1,317 @@
+// Weight-gradient implicit GEMM on tcgen05:
+//
+//   dw[t][co][ci] = sum_p dy[p, co] * x[p + off(t), ci]
+//
+// GEMM view: M = Cout (128-channel tile), N = Cin (BLOCK_N-channel tile), K = pixels. Both operands are
+// "MN-major" for the tensor core: a TMA box [64 ch, bw, bh, 1] lands as (pixels x 128 bytes) rows in
+// 128B-swizzled smem, which is exactly the canonical MN-major SWIZZLE_128B layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) with LBO = bytes per 64-channel box and SBO = 1024 (8 pixels).
+// Replaces cuDNN's wgrad behind autograd for every nn.Conv2d on the path (model/resnet.py:63-69).
+//
+// Work unit = (split, tap, co-tile, ci-tile); a split owns a contiguous range of pixel boxes.
+// K block = one pixel box of <= 64 pixels; the smem rows a box does not cover are zeroed once at kernel
+// start and never written again, so they contribute exact zeros.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace sb {
+
+constexpr int kWgThreads = 192;
+constexpr int kWgEpiThreads = 128;
+constexpr int kWgBoxPixels = 64;
+constexpr int kWgBoxBytes = kWgBoxPixels * 128;  // one 64-channel x 64-pixel box
+constexpr int kWgBlockN = 256;
+constexpr int kWgABoxes = 2;                      // 128 Cout channels
+constexpr int kWgBBoxes = kWgBlockN / 64;         // 256 Cin channels
+constexpr int kWgStageBytes = (kWgABoxes + kWgBBoxes) * kWgBoxBytes;  // 48 KB
+constexpr int kWgStages = 4;
+constexpr int kWgTmemCols = 2 * kWgBlockN;
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 1024;
+
+struct WgradKParams {
+  int N, H, W, Cin, Cout, taps;
+  int bh, bw, tiles_h, tiles_w, num_boxes;
+  int co_tiles, ci_tiles, n_splits, boxes_per_split;
+  int dh[SEMSEG_MAX_TAPS], dw[SEMSEG_MAX_TAPS], img_add[SEMSEG_MAX_TAPS];
+  int img_mul;
+  float* out;  // [n_splits][taps][Cout][Cin]
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                  const WgradKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* misc = smem + kWgStages * kWgStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);
+  uint64_t* empty_bar = full_bar + kWgStages;
+  uint64_t* tmem_full = empty_bar + kWgStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int units_per_split = p.taps * p.co_tiles * p.ci_tiles;
+  const int num_units = units_per_split * p.n_splits;
+  const uint32_t box_bytes = static_cast<uint32_t>(p.bh * p.bw) * 128u;
+  const uint32_t stage_tx = box_bytes * (kWgABoxes + kWgBBoxes);
+
+  // Zero all operand stages once: rows beyond the pixel box stay zero for the whole kernel.
+  {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* s4 = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < kWgStages * kWgStageBytes / 16; i += kWgThreads) s4[i] = z;
+  }
+  fence_proxy_async_smem();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kWgEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kWgTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // unit -> (split, tap, co_tile, ci_tile); ci fastest so concurrent CTAs share the dy boxes in L2
+  auto decode = [&](int unit, int& split, int& tap, int& co_t, int& ci_t) {
+    ci_t = unit % p.ci_tiles;
+    int r = unit / p.ci_tiles;
+    co_t = r % p.co_tiles;
+    r /= p.co_tiles;
+    tap = r % p.taps;
+    split = r / p.taps;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        int split, tap, co_t, ci_t;
+        decode(unit, split, tap, co_t, ci_t);
+        const int b0 = split * p.boxes_per_split;
+        const int b1 = min(b0 + p.boxes_per_split, p.num_boxes);
+        const int tiles_per_img = p.tiles_h * p.tiles_w;
+        for (int b = b0; b < b1; ++b, ++it) {
+          const int s = it % kWgStages;
+          const uint32_t par = (it / kWgStages) & 1;
+          mbar_wait(&empty_bar[s], par ^ 1);
+          const int img = b / tiles_per_img;
+          const int rem = b - img * tiles_per_img;
+          const int h0 = (rem / p.tiles_w) * p.bh;
+          const int w0 = (rem % p.tiles_w) * p.bw;
+          uint8_t* st = smem + s * kWgStageBytes;
+          mbar_expect_tx(&full_bar[s], stage_tx);
+#pragma unroll
+          for (int i = 0; i < kWgABoxes; ++i)
+            tma_load_4d(st + i * kWgBoxBytes, &tmDY, &full_bar[s], co_t * 128 + i * 64, w0, h0, img);
+#pragma unroll
+          for (int i = 0; i < kWgBBoxes; ++i)
+            tma_load_4d(st + (kWgABoxes + i) * kWgBoxBytes, &tmX, &full_bar[s], ci_t * kWgBlockN + i * 64,
+                        w0 + p.dw[tap], h0 + p.dh[tap], img * p.img_mul + p.img_add[tap]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, kWgBlockN, 1, 1);  // A and B MN-major
+      int it = 0;
+      int unit_iter = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++unit_iter) {
+        int split, tap, co_t, ci_t;
+        decode(unit, split, tap, co_t, ci_t);
+        const int b0 = split * p.boxes_per_split;
+        const int b1 = min(b0 + p.boxes_per_split, p.num_boxes);
+        const int as = unit_iter & 1;
+        const uint32_t apar = (unit_iter >> 1) & 1;
+        mbar_wait(&tmem_empty[as], apar ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kWgBlockN);
+        for (int b = b0; b < b1; ++b, ++it) {
+          const int s = it % kWgStages;
+          const uint32_t par = (it / kWgStages) & 1;
+          mbar_wait(&full_bar[s], par);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * kWgStageBytes);
+          const uint32_t b_addr = a_addr + kWgABoxes * kWgBoxBytes;
+          // MN-major SW128: LBO = next 64-channel box, SBO = next 8 pixels (1024 B)
+          const uint64_t adesc = make_smem_desc_sw128(a_addr, kWgBoxBytes, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(b_addr, kWgBoxBytes, 1024);
+#pragma unroll
+          for (int k = 0; k < kWgBoxPixels / 16; ++k) {
+            // 16 pixels along K = 2048 bytes -> +128 in 16-byte units
+            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 128), bdesc + static_cast<uint64_t>(k * 128), idesc,
+                      (b > b0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    const int g = warp & 3;
+    const int row = g * 32 + lane;  // Cout index within the tile
+    int unit_iter = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++unit_iter) {
+      int split, tap, co_t, ci_t;
+      decode(unit, split, tap, co_t, ci_t);
+      const int as = unit_iter & 1;
+      const uint32_t apar = (unit_iter >> 1) & 1;
+      mbar_wait(&tmem_full[as], apar);
+      tc_fence_after();
+      const int co = co_t * 128 + row;
+      const int ci0 = ci_t * kWgBlockN;
+      float* orow = p.out + ((static_cast<size_t>(split) * p.taps + tap) * p.Cout + co) * p.Cin + ci0;
+#pragma unroll 1
+      for (int ch = 0; ch < kWgBlockN / 32; ++ch) {
+        if (ci0 + ch * 32 >= p.Cin) break;
+        uint32_t v[32];
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(g * 32) << 16) + static_cast<uint32_t>(as * kWgBlockN + ch * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          if (ci0 + ch * 32 + 32 <= p.Cin && (p.Cin & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 f = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                     __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+              *reinterpret_cast<float4*>(orow + ch * 32 + 4 * q) = f;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (ci0 + ch * 32 + q < p.Cin) orow[ch * 32 + q] = __uint_as_float(v[q]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kWgTmemCols>(tmem_base);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int n_splits, int taps, int Cout, int Cin,
+                                    float* __restrict__ dw, int accumulate) {
+  // one thread per (co, ci); loops taps. part[s][t][co][ci] -> dw[co][ci][t]
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t plane = static_cast<size_t>(Cout) * Cin;
+  if (idx >= plane) return;
+  for (int t = 0; t < taps; ++t) {
+    float s = 0.f;
+    for (int sp = 0; sp < n_splits; ++sp) s += part[(static_cast<size_t>(sp) * taps + t) * plane + idx];
+    float* d = dw + idx * taps + t;
+    *d = accumulate ? (*d + s) : s;
+  }
+}
+
+static void wgrad_geometry(const semseg_wgrad_desc* d, WgradKParams* kp) {
+  kp->N = d->N; kp->H = d->H; kp->W = d->W; kp->Cin = d->Cin; kp->Cout = d->Cout; kp->taps = d->taps;
+  choose_box(d->H, d->W, kWgBoxPixels, &kp->bh, &kp->bw);
+  kp->tiles_h = cdiv(d->H, kp->bh);
+  kp->tiles_w = cdiv(d->W, kp->bw);
+  kp->num_boxes = d->N * kp->tiles_h * kp->tiles_w;
+  kp->co_tiles = cdiv(d->Cout, 128);
+  kp->ci_tiles = cdiv(d->Cin, kWgBlockN);
+  const int units = d->taps * kp->co_tiles * kp->ci_tiles;
+  int splits = d->n_splits;
+  if (splits <= 0) {
+    // aim for >= 2 waves of work units over the SMs, but keep >= 16 K-blocks per unit
+    const int target = 2 * num_sms();
+    splits = cdiv(target, units);
+    const int max_by_k = kp->num_boxes / 16 > 0 ? kp->num_boxes / 16 : 1;
+    if (splits > max_by_k) splits = max_by_k;
+    if (splits > 64) splits = 64;
+    if (splits < 1) splits = 1;
+  }
+  kp->boxes_per_split = cdiv(kp->num_boxes, splits);
+  kp->n_splits = cdiv(kp->num_boxes, kp->boxes_per_split);  // no empty splits
+}
+
+}  // namespace sb
+
+extern "C" int semseg_conv_wgrad_splits(const semseg_wgrad_desc* d) {
+  if (!d || d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0) return SEMSEG_E_INVALID;
+  sb::WgradKParams kp;
+  sb::wgrad_geometry(d, &kp);
+  return kp.n_splits;
+}
+
+extern "C" int semseg_conv_wgrad(const semseg_wgrad_desc* d, void* stream_) {
+  using namespace sb;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(d != nullptr, "wgrad: null descriptor");
+  SB_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "wgrad: bad sizes");
+  SB_CHECK_ARG(d->taps >= 1 && d->taps <= SEMSEG_MAX_TAPS, "wgrad: taps out of range");
+  SB_CHECK_ARG(d->x && d->dy && d->dw_partial, "wgrad: null pointer");
+  SB_CHECK_ARG(d->x_pitch % 8 == 0 && d->dy_pitch % 8 == 0, "wgrad: pitches must be multiples of 8");
+  WgradKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  wgrad_geometry(d, &kp);
+  if (d->n_splits > 0)
+    SB_CHECK_ARG(kp.n_splits == d->n_splits, "wgrad: n_splits %d not realisable (library would use %d)",
+                 d->n_splits, kp.n_splits);
+  for (int t = 0; t < d->taps; ++t) {
+    kp.dh[t] = d->dh[t]; kp.dw[t] = d->dw[t]; kp.img_add[t] = d->img_add[t];
+  }
+  kp.img_mul = d->img_mul;
+  kp.out = d->dw_partial;
+
+  CUtensorMap tmDY, tmX;
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)d->dy_pitch * 2, (uint64_t)d->dy_pitch * 2 * d->W,
+                       (uint64_t)d->dy_pitch * 2 * d->W * d->H};
+    uint32_t box[4] = {64u, (uint32_t)kp.bw, (uint32_t)kp.bh, 1};
+    int r = encode_tmap_bf16(&tmDY, d->dy, 4, dims, str, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->Nin};
+    uint64_t str[3] = {(uint64_t)d->x_pitch * 2, (uint64_t)d->x_pitch * 2 * d->Win,
+                       (uint64_t)d->x_pitch * 2 * d->Win * d->Hin};
+    uint32_t box[4] = {64u, (uint32_t)kp.bw, (uint32_t)kp.bh, 1};
+    int r = encode_tmap_bf16(&tmX, d->x, 4, dims, str, box);
+    if (r) return r;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    attr_set = true;
+  }
+  const int units = kp.taps * kp.co_tiles * kp.ci_tiles * kp.n_splits;
+  const int grid = units < num_sms() ? units : num_sms();
+  conv_wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(tmDY, tmX, kp);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_wgrad_reduce(const float* dw_partial, int n_splits, int taps, int Cout, int Cin,
+                                   float* dw_oihw, int accumulate, void* stream_) {
+  using namespace sb;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(dw_partial && dw_oihw && n_splits > 0 && taps > 0 && Cout > 0 && Cin > 0, "wgrad_reduce: bad args");
+  const size_t plane = static_cast<size_t>(Cout) * Cin;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((plane + threads - 1) / threads);
+  wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(dw_partial, n_splits, taps, Cout, Cin, dw_oihw, accumulate);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}

@@ -1,0 +1,138 @@
+// Layout conversion at the module boundary and weight packing.
+//   - NCHW fp32 <-> NHWC bf16 / fp32 (model/pspnet.py:80-105 takes and returns NCHW fp32)
+//   - fp32 OIHW master weights -> bf16 [tap][row][col] operand slabs for the implicit-GEMM kernels
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace sb {
+
+// 32x32 tiled transpose between [C][HW] (NCHW plane) and [HW][pitch] (NHWC) per image.
+template <typename TIn, typename TOut>
+__global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int C, int HW, int out_pitch) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const TIn* src = in + static_cast<size_t>(n) * C * HW;
+  TOut* dst = out + static_cast<size_t>(n) * HW * out_pitch;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < C && p < HW) ? static_cast<float>(src[static_cast<size_t>(c) * HW + p]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    if (p < HW && c < C) dst[static_cast<size_t>(p) * out_pitch + c] = static_cast<TOut>(tile[threadIdx.x][r]);
+  }
+}
+
+template <typename TIn, typename TOut>
+__global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int C, int HW, int in_pitch) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const TIn* src = in + static_cast<size_t>(n) * HW * in_pitch;
+  TOut* dst = out + static_cast<size_t>(n) * C * HW;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < HW && c < C) ? static_cast<float>(src[static_cast<size_t>(p) * in_pitch + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    if (c < C && p < HW) dst[static_cast<size_t>(c) * HW + p] = static_cast<TOut>(tile[threadIdx.x][r]);
+  }
+}
+
+// w[co][ci][t] fp32 -> wf[t][co][ci] bf16 (rows_f x cols_f, zero padded). One thread per output element.
+__global__ void pack_wf_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, __nv_bfloat16* __restrict__ wf,
+                               int rows, int cols) {
+  const size_t total = static_cast<size_t>(taps) * rows * cols;
+  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(idx % cols);
+    const size_t r = idx / cols;
+    const int co = static_cast<int>(r % rows);
+    const int t = static_cast<int>(r / rows);
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[(static_cast<size_t>(co) * Cin + ci) * taps + t];
+    wf[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// w[co][ci][t] fp32 -> wd[t][ci][co] bf16 via a 32x32 smem transpose of the (co, ci) plane per tap.
+__global__ void pack_wd_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, __nv_bfloat16* __restrict__ wd,
+                               int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    tile[r][threadIdx.x] = (co < Cout && ci < Cin) ? w[(static_cast<size_t>(co) * Cin + ci) * taps + t] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < rows && co < cols)
+      wd[(static_cast<size_t>(t) * rows + ci) * cols + co] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+  }
+}
+
+}  // namespace sb
+
+using namespace sb;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int semseg_pack_weights(const float* w_oihw, int Cout, int Cin, int taps, void* wf, int rows_f, int cols_f,
+                                   void* wd, int rows_d, int cols_d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(w_oihw && Cout > 0 && Cin > 0 && taps > 0 && taps <= SEMSEG_MAX_TAPS, "pack_weights: bad args");
+  if (wf) {
+    SB_CHECK_ARG(rows_f >= Cout && cols_f >= Cin && cols_f % 8 == 0, "pack_weights: bad wf dims %d x %d", rows_f,
+                 cols_f);
+    const size_t total = static_cast<size_t>(taps) * rows_f * cols_f;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    pack_wf_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(w_oihw, Cout, Cin, taps, static_cast<bf16*>(wf),
+                                                                     rows_f, cols_f);
+    SB_LAUNCHED();
+  }
+  if (wd) {
+    SB_CHECK_ARG(rows_d >= Cin && cols_d >= Cout && cols_d % 8 == 0, "pack_weights: bad wd dims %d x %d", rows_d,
+                 cols_d);
+    dim3 grid(cdiv(rows_d, 32), cdiv(cols_d, 32), taps);
+    pack_wd_kernel<<<grid, dim3(32, 8), 0, stream>>>(w_oihw, Cout, Cin, taps, static_cast<bf16*>(wd), rows_d, cols_d);
+    SB_LAUNCHED();
+  }
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_nchw_f32_to_nhwc_bf16(const float* in, void* out, int N, int C, int H, int W, int out_pitch,
+                                            void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && out_pitch >= C, "nchw_f32_to_nhwc_bf16: bad args");
+  dim3 grid(cdiv(H * W, 32), cdiv(C, 32), N);
+  nchw_to_nhwc_kernel<float, bf16><<<grid, dim3(32, 8), 0, stream>>>(in, static_cast<bf16*>(out), C, H * W, out_pitch);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_nhwc_bf16_to_nchw_f32(const void* in, float* out, int N, int C, int H, int W, int in_pitch,
+                                            void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && in_pitch >= C, "nhwc_bf16_to_nchw_f32: bad args");
+  dim3 grid(cdiv(H * W, 32), cdiv(C, 32), N);
+  nhwc_to_nchw_kernel<bf16, float><<<grid, dim3(32, 8), 0, stream>>>(static_cast<const bf16*>(in), out, C, H * W,
+                                                                    in_pitch);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_nhwc_f32_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W, int in_pitch,
+                                           void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && in_pitch >= C, "nhwc_f32_to_nchw_f32: bad args");
+  dim3 grid(cdiv(H * W, 32), cdiv(C, 32), N);
+  nhwc_to_nchw_kernel<float, float><<<grid, dim3(32, 8), 0, stream>>>(in, out, C, H * W, in_pitch);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}

@@ -1,0 +1,352 @@
+"""Tensor-level wrappers over the C-ABI (semseg_b200/_lib.py): every function takes CUDA tensors,
+launches on torch's current stream and returns tensors. PyTorch is used for device memory and streams
+only; the arithmetic happens in libsemseg_b200.so. No function here has a CPU or eager fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, WgradDesc, EPI_RAW, EPI_AFFINE, EPI_F32, MAX_TAPS
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.SemsegError("semseg_b200 ops require CUDA tensors (no CPU fallback); got device %s" % t.device)
+
+
+def _nhwc_meta(t):
+    """(N, H, W, C, pitch) of a bf16 NHWC tensor whose channel dim may be a slice of a wider buffer."""
+    assert t.dim() == 4 and t.dtype == torch.bfloat16, (t.shape, t.dtype)
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    assert sc == 1 and sh == sw * w and sn == sh * h, "NHWC tensor must be pixel-contiguous (stride %s)" % (t.stride(),)
+    return n, h, w, c, sw
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+# ------------------------------------------------------------------------------------------------ psa mask
+def psamask_fwd(x, psa_type, mask_h, mask_w):
+    _require_cuda(x)
+    lib = _lib.load()
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty((n, h * w, h, w), dtype=torch.float32, device=x.device)
+    _lib.check(lib.semseg_psamask_fwd(psa_type, _ptr(x), _ptr(out), n, h, w, mask_h, mask_w, _stream()),
+               "semseg_psamask_fwd")
+    return out
+
+
+def psamask_bwd(grad_out, psa_type, mask_h, mask_w):
+    _require_cuda(grad_out)
+    lib = _lib.load()
+    assert grad_out.dtype == torch.float32 and grad_out.is_contiguous()
+    n, hw, h, w = grad_out.shape
+    din = torch.empty((n, mask_h * mask_w, h, w), dtype=torch.float32, device=grad_out.device)
+    _lib.check(lib.semseg_psamask_bwd(psa_type, _ptr(grad_out), _ptr(din), n, h, w, mask_h, mask_w, _stream()),
+               "semseg_psamask_bwd")
+    return din
+
+
+# ------------------------------------------------------------------------------------------------ weights
+class PackedWeight:
+    """bf16 operand slabs of one conv weight: wf [taps][Cout][Cin_p] (fprop), wd [taps][Cin][Cout_p] (dgrad)."""
+    __slots__ = ("wf", "wd", "cout", "cin", "taps", "ksize")
+
+    def __init__(self, wf, wd, cout, cin, taps, ksize):
+        self.wf, self.wd, self.cout, self.cin, self.taps, self.ksize = wf, wd, cout, cin, taps, ksize
+
+
+def pack_weights(w, need_dgrad=True):
+    """w: fp32 OIHW parameter -> PackedWeight (one fused launch pair)."""
+    _require_cuda(w)
+    lib = _lib.load()
+    w = w.detach()
+    assert w.dtype == torch.float32 and w.dim() == 4
+    if not w.is_contiguous():
+        w = w.contiguous()
+    cout, cin, kh, kw = w.shape
+    assert kh == kw
+    taps = kh * kw
+    cin_p, cout_p = round_up(cin, 8), round_up(cout, 8)
+    wf = torch.empty((taps, cout, cin_p), dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty((taps, cin, cout_p), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
+    _lib.check(lib.semseg_pack_weights(_ptr(w), cout, cin, taps, _ptr(wf), cout, cin_p, _ptr(wd),
+                                       cin if need_dgrad else 0, cout_p if need_dgrad else 0, _stream()),
+               "semseg_pack_weights")
+    return PackedWeight(wf, wd, cout, cin, taps, kh)
+
+
+def conv_taps(ksize, dilation, transpose=False):
+    """[(dh, dw, wtap)] of a stride-1 'same' conv; transpose=True gives the dgrad taps."""
+    taps = []
+    half = ksize // 2
+    for r in range(ksize):
+        for s in range(ksize):
+            dh, dw = (r - half) * dilation, (s - half) * dilation
+            if transpose:
+                dh, dw = -dh, -dw
+            taps.append((dh, dw, r * ksize + s))
+    return taps
+
+
+def _fill_taps(desc, taps, with_wtap=True):
+    assert 1 <= len(taps) <= MAX_TAPS
+    desc.taps = len(taps)
+    for i, t in enumerate(taps):
+        desc.dh[i], desc.dw[i] = t[0], t[1]
+        if with_wtap:
+            desc.wtap[i] = t[2]
+        desc.img_add[i] = 0
+    desc.img_mul = 1
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def conv_num_m_tiles(n, h, w):
+    return int(_lib.load().semseg_conv_num_m_tiles(n, h, w))
+
+
+def conv_fprop(x, w3d, cout, taps, *, out=None, epi=EPI_RAW, relu=False, scale=None, shift=None, residual=None,
+               stats=False, out_f32=None):
+    """Implicit-GEMM conv of NHWC bf16 `x` with packed weights `w3d` [n_wtaps][rows][cols].
+
+    Returns (y, stats_partial, tile_count); y is bf16 NHWC [N,H,W,cout] (or the fp32 tensor in F32 mode).
+    """
+    _require_cuda(x, w3d)
+    lib = _lib.load()
+    n, h, w, cin, xp = _nhwc_meta(x)
+    d = ConvDesc()
+    d.N, d.H, d.W, d.Cin, d.Cout = n, h, w, cin, cout
+    d.x, d.Nin, d.Hin, d.Win, d.x_pitch = x.data_ptr(), n, h, w, xp
+    assert w3d.dtype == torch.bfloat16 and w3d.is_contiguous() and w3d.dim() == 3
+    d.w, d.n_wtaps, d.w_rows, d.w_cols = w3d.data_ptr(), w3d.shape[0], w3d.shape[1], w3d.shape[2]
+    _fill_taps(d, taps)
+    d.epi_mode, d.relu = epi, int(bool(relu))
+    sp = tc = None
+    if epi == EPI_F32:
+        if out_f32 is None:
+            out_f32 = torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
+        assert out_f32.dtype == torch.float32 and out_f32.stride(-1) == 1
+        d.out_f32, d.out_pitch = out_f32.data_ptr(), out_f32.stride(2)
+        y = out_f32
+    else:
+        if out is None:
+            out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x.device)
+        on, oh, ow, oc, op = _nhwc_meta(out)
+        assert (on, oh, ow, oc) == (n, h, w, cout)
+        d.y, d.y_pitch = out.data_ptr(), op
+        y = out
+    if scale is not None:
+        assert scale.dtype == torch.float32 and scale.numel() >= cout
+        d.scale = scale.data_ptr()
+    if shift is not None:
+        assert shift.dtype == torch.float32 and shift.numel() >= cout
+        d.shift = shift.data_ptr()
+    if residual is not None:
+        rn, rh, rw, rc, rp = _nhwc_meta(residual)
+        assert (rn, rh, rw, rc) == (n, h, w, cout)
+        d.residual, d.res_pitch = residual.data_ptr(), rp
+    if stats:
+        assert epi == EPI_RAW
+        mt = conv_num_m_tiles(n, h, w)
+        sp = torch.empty((mt, 2, cout), dtype=torch.float32, device=x.device)
+        tc = torch.empty((mt,), dtype=torch.float32, device=x.device)
+        d.stats_partial, d.tile_count = sp.data_ptr(), tc.data_ptr()
+    _lib.check(lib.semseg_conv_fprop(ctypes.byref(d), _stream()), "semseg_conv_fprop")
+    return y, sp, tc
+
+
+def conv_wgrad(x, dy, cin, cout, taps, grad_out=None, accumulate=False):
+    """dW (fp32 OIHW [cout][cin][k][k]) of a stride-1 conv from NHWC bf16 x and dy."""
+    _require_cuda(x, dy)
+    lib = _lib.load()
+    n, h, w, xc, xp = _nhwc_meta(x)
+    dn, dh_, dw_, dc, dp = _nhwc_meta(dy)
+    assert (dn, dh_, dw_) == (n, h, w) and xc >= cin and dc >= cout
+    d = WgradDesc()
+    d.N, d.H, d.W, d.Cin, d.Cout = n, h, w, cin, cout
+    d.x, d.Nin, d.Hin, d.Win, d.x_pitch = x.data_ptr(), n, h, w, xp
+    d.dy, d.dy_pitch = dy.data_ptr(), dp
+    _fill_taps(d, taps, with_wtap=False)
+    d.n_splits = 0
+    splits = lib.semseg_conv_wgrad_splits(ctypes.byref(d))
+    if splits <= 0:
+        raise _lib.SemsegError("semseg_conv_wgrad_splits failed (%d)" % splits)
+    ntaps = len(taps)
+    part = torch.empty((splits, ntaps, cout, cin), dtype=torch.float32, device=x.device)
+    d.dw_partial = part.data_ptr()
+    d.n_splits = splits
+    _lib.check(lib.semseg_conv_wgrad(ctypes.byref(d), _stream()), "semseg_conv_wgrad")
+    k = int(round(ntaps ** 0.5))
+    if grad_out is None:
+        grad_out = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.device)
+        accumulate = False
+    assert grad_out.is_contiguous() and grad_out.dtype == torch.float32
+    _lib.check(lib.semseg_wgrad_reduce(_ptr(part), splits, ntaps, cout, cin, _ptr(grad_out), int(accumulate),
+                                       _stream()), "semseg_wgrad_reduce")
+    return grad_out
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def nchw_to_nhwc_bf16(x, pad_to=8):
+    _require_cuda(x)
+    lib = _lib.load()
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n, c, h, w = x.shape
+    cp = round_up(c, pad_to)
+    out = (torch.zeros if cp != c else torch.empty)((n, h, w, cp), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.semseg_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(out), n, c, h, w, cp, _stream()),
+               "semseg_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_bf16_to_nchw(x):
+    _require_cuda(x)
+    lib = _lib.load()
+    n, h, w, c, p = _nhwc_meta(x)
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _lib.check(lib.semseg_nhwc_bf16_to_nchw_f32(_ptr(x), _ptr(out), n, c, h, w, p, _stream()),
+               "semseg_nhwc_bf16_to_nchw_f32")
+    return out
+
+
+def nhwc_f32_to_nchw(x):
+    _require_cuda(x)
+    lib = _lib.load()
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.stride(-1) == 1
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _lib.check(lib.semseg_nhwc_f32_to_nchw_f32(_ptr(x), _ptr(out), n, c, h, w, x.stride(2), _stream()),
+               "semseg_nhwc_f32_to_nchw_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ batch norm
+def bn_workspace(m, c, device):
+    nf = int(_lib.load().semseg_bn_workspace_floats(m, c))
+    return torch.empty((nf,), dtype=torch.float32, device=device), nf
+
+
+def bn_merge_partials(stats_partial, tile_count):
+    lib = _lib.load()
+    t, _, c = stats_partial.shape
+    out = torch.empty((3, c), dtype=torch.float32, device=stats_partial.device)
+    _lib.check(lib.semseg_bn_merge_partials(_ptr(stats_partial), _ptr(tile_count), t, c, _ptr(out), _stream()),
+               "semseg_bn_merge_partials")
+    return out
+
+
+def bn_stats(x):
+    """(mean, M2, count) [3][C] of an NHWC bf16 tensor."""
+    _require_cuda(x)
+    lib = _lib.load()
+    n, h, w, c, p = _nhwc_meta(x)
+    m = n * h * w
+    ws, nf = bn_workspace(m, c, x.device)
+    out = torch.empty((3, c), dtype=torch.float32, device=x.device)
+    _lib.check(lib.semseg_bn_stats(_ptr(x), m, c, p, _ptr(ws), nf, _ptr(out), _stream()), "semseg_bn_stats")
+    return out
+
+
+def bn_finalize(rank_stats, gamma, beta, eps, momentum, running_mean, running_var):
+    """rank_stats [R][3][C] -> (mean_invstd [2][C], scale_shift [2][C]); updates running stats in place."""
+    lib = _lib.load()
+    if rank_stats.dim() == 2:
+        rank_stats = rank_stats.unsqueeze(0)
+    r, _, c = rank_stats.shape
+    assert rank_stats.is_contiguous()
+    mi = torch.empty((2, c), dtype=torch.float32, device=rank_stats.device)
+    ss = torch.empty((2, c), dtype=torch.float32, device=rank_stats.device)
+    _lib.check(lib.semseg_bn_finalize(_ptr(rank_stats), r, c, _ptr(gamma), _ptr(beta), float(eps), float(momentum),
+                                      _ptr(running_mean), _ptr(running_var), _ptr(mi), _ptr(ss), _stream()),
+               "semseg_bn_finalize")
+    return mi, ss
+
+
+def bn_fold_eval(gamma, beta, running_mean, running_var, eps):
+    lib = _lib.load()
+    c = running_mean.numel()
+    ss = torch.empty((2, c), dtype=torch.float32, device=running_mean.device)
+    _lib.check(lib.semseg_bn_fold_eval(_ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), float(eps), c,
+                                       _ptr(ss), _stream()), "semseg_bn_fold_eval")
+    return ss
+
+
+def bn_apply(x, scale_shift, residual=None, relu=True, out=None):
+    _require_cuda(x)
+    lib = _lib.load()
+    n, h, w, c, xp = _nhwc_meta(x)
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    _, _, _, oc, op = _nhwc_meta(out)
+    assert oc == c
+    rp = 0
+    if residual is not None:
+        _, _, _, rc, rp = _nhwc_meta(residual)
+        assert rc == c
+    _lib.check(lib.semseg_bn_apply(_ptr(x), xp, _ptr(scale_shift), _ptr(residual), rp, _ptr(out), op, n * h * w, c,
+                                   int(bool(relu)), _stream()), "semseg_bn_apply")
+    return out
+
+
+def bn_bwd_reduce(dy, y, x, mean_invstd, relu):
+    lib = _lib.load()
+    n, h, w, c, dp = _nhwc_meta(dy)
+    _, _, _, _, xp = _nhwc_meta(x)
+    yp = _nhwc_meta(y)[4] if y is not None else 0
+    m = n * h * w
+    ws, nf = bn_workspace(m, c, dy.device)
+    sums = torch.empty((2, c), dtype=torch.float32, device=dy.device)
+    _lib.check(lib.semseg_bn_bwd_reduce(_ptr(dy), dp, _ptr(y), yp, _ptr(x), xp, _ptr(mean_invstd), m, c,
+                                        int(bool(relu)), _ptr(ws), nf, _ptr(sums), _stream()),
+               "semseg_bn_bwd_reduce")
+    return sums
+
+
+def bn_bwd_apply(dy, y, x, mean_invstd, gamma, sums, count, relu, want_dres=False):
+    """Returns (dx bf16, dres bf16 or None, dgamma_dbeta [2][C])."""
+    lib = _lib.load()
+    n, h, w, c, dp = _nhwc_meta(dy)
+    _, _, _, _, xp = _nhwc_meta(x)
+    yp = _nhwc_meta(y)[4] if y is not None else 0
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
+    dres = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device) if want_dres else None
+    dgb = torch.empty((2, c), dtype=torch.float32, device=dy.device)
+    _lib.check(lib.semseg_bn_bwd_apply(_ptr(dy), dp, _ptr(y), yp, _ptr(x), xp, _ptr(mean_invstd), _ptr(gamma),
+                                       _ptr(sums), float(count), n * h * w, c, int(bool(relu)), _ptr(dx), c,
+                                       _ptr(dres), c, _ptr(dgb), _stream()), "semseg_bn_bwd_apply")
+    return dx, dres, dgb
+
+
+def relu_bwd(dy, y):
+    lib = _lib.load()
+    n, h, w, c, dp = _nhwc_meta(dy)
+    yp = _nhwc_meta(y)[4]
+    dz = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
+    _lib.check(lib.semseg_relu_bwd(_ptr(dy), dp, _ptr(y), yp, _ptr(dz), c, n * h * w, c, _stream()),
+               "semseg_relu_bwd")
+    return dz
+
+
+def add_bf16(a, b, out=None):
+    lib = _lib.load()
+    n, h, w, c, ap = _nhwc_meta(a)
+    bp = _nhwc_meta(b)[4]
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=a.device)
+    op = _nhwc_meta(out)[4]
+    _lib.check(lib.semseg_add_bf16(_ptr(a), ap, _ptr(b), bp, _ptr(out), op, n * h * w, c, _stream()),
+               "semseg_add_bf16")
+    return out
