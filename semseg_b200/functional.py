@@ -1,0 +1,239 @@
+"""Autograd functions of the hot path, operating on NHWC bf16 activations.
+
+Each Function is a thin scheduler of C-ABI kernel launches (semseg_b200/ops.py); the fp32 master weights
+stay ordinary nn.Parameters (OIHW) so torch.optim.SGD, DistributedDataParallel and state_dict see exactly
+what the reference's modules expose (tool/train.py:134-140,157).
+
+conv + BatchNorm(train) + ReLU (+ residual) is three launches forward:
+    conv_fprop (raw bf16 + per-tile partial statistics)  ->  bn_merge/finalize  ->  bn_apply
+because training-mode BN needs the batch (and, under SyncBN, cross-rank) statistics of the complete conv
+output before anything can be normalised (model/resnet.py:77-83). In eval mode the BN folds into the conv
+epilogue and the whole thing is a single kernel.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .dist_utils import gather_rank_stats
+from .ops import EPI_RAW, EPI_AFFINE, EPI_F32
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def packed(conv, need_dgrad=True):
+    """bf16 operand slabs of conv.weight, re-packed only when the parameter changed (optimizer step / load)."""
+    w = conv.weight
+    key = (w._version, w.data_ptr(), need_dgrad)
+    cache = conv.__dict__.get("_sb_pack")
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    pw = ops.pack_weights(w, need_dgrad=need_dgrad)
+    conv.__dict__["_sb_pack"] = (key, pw)
+    return pw
+
+
+def _sync_group(bn):
+    """Process group when `bn` is a SyncBatchNorm that must synchronise, else None."""
+    if isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized():
+        pg = bn.process_group if bn.process_group is not None else dist.group.WORLD
+        if dist.get_world_size(pg) > 1:
+            return pg
+    return None
+
+
+def _bn_momentum(bn):
+    # nn.BatchNorm semantics: momentum None = cumulative moving average
+    if bn.momentum is None:
+        return 1.0 / float(bn.num_batches_tracked.item() + 1)
+    return bn.momentum
+
+
+def _finalize_stats(stats, bn, pg):
+    """stats [3][C] local (mean, M2, count) -> (mean_invstd, scale_shift, world). Updates running stats."""
+    world = 1
+    if pg is not None:
+        world = dist.get_world_size(pg)
+        stats = gather_rank_stats(stats, pg)
+    track = bn.track_running_stats and bn.running_mean is not None
+    mom = _bn_momentum(bn) if track else 0.0
+    mi, ss = ops.bn_finalize(stats, bn.weight, bn.bias, bn.eps, mom, bn.running_mean if track else None,
+                             bn.running_var if track else None)
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return mi, ss, world
+
+
+def _bn_backward(ctx_pg, world, dy, y, raw, mi, gamma, relu, want_dres):
+    """Shared BN(+ReLU) backward: returns (d_raw, dres, dgamma, dbeta)."""
+    n, h, w, c = raw.shape
+    if not dy.is_contiguous():
+        dy = dy.contiguous()
+    sums = ops.bn_bwd_reduce(dy, y if relu else None, raw, mi, relu)
+    dbeta, dgamma = sums[0], sums[1]
+    if ctx_pg is not None:
+        dbeta, dgamma = dbeta.clone(), dgamma.clone()  # local sums feed dgamma/dbeta (DDP averages them)
+        dist.all_reduce(sums, group=ctx_pg)
+    count = float(n * h * w * world)
+    d_raw, dres, _ = ops.bn_bwd_apply(dy, y if relu else None, raw, mi, gamma, sums, count, relu, want_dres=want_dres)
+    return d_raw, dres, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------------ conv+bn+act
+class _ConvBnAct(torch.autograd.Function):
+    """Stride-1 conv (1x1 / 3x3, any dilation) + training BatchNorm + optional residual + optional ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, residual, conv, bn, relu, out):
+        pw = packed(conv)
+        k, dil = conv.kernel_size[0], conv.dilation[0]
+        raw, sp, tc = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(k, dil), stats=True)
+        stats = ops.bn_merge_partials(sp, tc)
+        pg = _sync_group(bn)
+        mi, ss, world = _finalize_stats(stats, bn, pg)
+        y = ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)
+        ctx.save_for_backward(x, raw, y if relu else None, mi, gamma)
+        ctx.pw, ctx.k, ctx.dil, ctx.relu, ctx.pg, ctx.world = pw, k, dil, relu, pg, world
+        ctx.has_res = residual is not None
+        if out is not None:
+            ctx.mark_dirty(out)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, raw, y, mi, gamma = ctx.saved_tensors
+        pw = ctx.pw
+        d_raw, dres, dgamma, dbeta = _bn_backward(ctx.pg, ctx.world, dy, y, raw, mi, gamma, ctx.relu,
+                                                  ctx.has_res and ctx.needs_input_grad[4])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx, _, _ = ops.conv_fprop(d_raw, pw.wd, pw.cin, ops.conv_taps(ctx.k, ctx.dil, transpose=True))
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_wgrad(x, d_raw, pw.cin, pw.cout, ops.conv_taps(ctx.k, ctx.dil))
+        return dx, dw, dgamma, dbeta, dres, None, None, None, None
+
+
+class _BnAct(torch.autograd.Function):
+    """Training BatchNorm + optional residual + optional ReLU on a raw NHWC bf16 tensor."""
+
+    @staticmethod
+    def forward(ctx, raw, gamma, beta, residual, bn, relu):
+        stats = ops.bn_stats(raw)
+        pg = _sync_group(bn)
+        mi, ss, world = _finalize_stats(stats, bn, pg)
+        y = ops.bn_apply(raw, ss, residual=residual, relu=relu)
+        ctx.save_for_backward(raw, y if relu else None, mi, gamma)
+        ctx.relu, ctx.pg, ctx.world, ctx.has_res = relu, pg, world, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        raw, y, mi, gamma = ctx.saved_tensors
+        d_raw, dres, dgamma, dbeta = _bn_backward(ctx.pg, ctx.world, dy, y, raw, mi, gamma, ctx.relu,
+                                                  ctx.has_res and ctx.needs_input_grad[3])
+        return d_raw, dgamma, dbeta, dres, None, None
+
+
+def _is_native_conv(conv, cin):
+    return (conv.kernel_size in ((1, 1), (3, 3)) and conv.stride == (1, 1) and conv.groups == 1 and
+            conv.padding == (conv.dilation[0] * (conv.kernel_size[0] // 2),) * 2 and
+            conv.dilation[0] == conv.dilation[1] and cin % 8 == 0 and conv.out_channels % 64 == 0 and
+            conv.bias is None)
+
+
+def _library_conv(x, conv):
+    """cuDNN channels-last bf16 path for the three convs the tensor-core kernel does not cover yet
+    (3-channel stem conv and the two stride-2 convs of layer2.0: 0.7 % of the network's FLOPs)."""
+    xn = x.permute(0, 3, 1, 2)  # NCHW view of the NHWC buffer (= channels_last)
+    if xn.shape[1] != conv.in_channels:
+        xn = xn[:, :conv.in_channels]
+    y = F.conv2d(xn, conv.weight.to(torch.bfloat16), None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def conv_bn_act(x, conv, bn, relu=True, residual=None, out=None):
+    """NHWC bf16 -> NHWC bf16: conv -> BatchNorm -> (+residual) -> (ReLU), training or eval semantics of `bn`."""
+    use_batch_stats = bn.training or (bn.running_mean is None)
+    native = _is_native_conv(conv, x.shape[-1])
+    if not use_batch_stats:
+        ss = ops.bn_fold_eval(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+        if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+            raise NotImplementedError("semseg_b200: gradients through eval-mode BatchNorm are not supported; "
+                                      "run eval under torch.no_grad()")
+        if native:
+            pw = packed(conv, need_dgrad=False)
+            y, _, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(conv.kernel_size[0], conv.dilation[0]),
+                                     epi=EPI_AFFINE, relu=relu, scale=ss[0], shift=ss[1], residual=residual, out=out)
+            return y
+        raw = _library_conv(x, conv)
+        return ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)
+    if native:
+        return _ConvBnAct.apply(x, conv.weight, bn.weight, bn.bias, residual, conv, bn, relu, out)
+    raw = _library_conv(x, conv)
+    y = _BnAct.apply(raw, bn.weight, bn.bias, residual, bn, relu)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ classifier
+class _ConvBiasF32(torch.autograd.Function):
+    """1x1 conv with bias producing fp32 NHWC logits (model/pspnet.py:69,77)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, conv):
+        pw = packed(conv)
+        y, _, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(1, 1), epi=EPI_F32, shift=bias)
+        ctx.save_for_backward(x)
+        ctx.pw = pw
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        pw = ctx.pw
+        n, h, w, c = dy.shape
+        cp = pw.wd.shape[2]  # Cout rounded up to 8 (zero padded operand)
+        dyb = torch.zeros((n, h, w, cp), dtype=torch.bfloat16, device=dy.device)
+        dyb[..., :c] = dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx, _, _ = ops.conv_fprop(dyb, pw.wd, pw.cin, ops.conv_taps(1, 1))
+        if ctx.needs_input_grad[1]:
+            dwp = ops.conv_wgrad(x, dyb, pw.cin, cp, ops.conv_taps(1, 1))
+            dw = dwp[:c].contiguous()
+        if ctx.needs_input_grad[2]:
+            db = dy.sum(dim=(0, 1, 2))
+        return dx, dw, db, None
+
+
+def conv_bias_f32(x, conv):
+    assert conv.kernel_size == (1, 1) and conv.stride == (1, 1) and x.shape[-1] % 8 == 0
+    if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+        return _ConvBiasF32.apply(x, conv.weight, conv.bias, conv)
+    pw = packed(conv, need_dgrad=False)
+    y, _, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(1, 1), epi=EPI_F32, shift=conv.bias)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ misc NHWC ops
+def to_nhwc_bf16(x_nchw):
+    """fp32 NCHW module input -> bf16 NHWC (channels padded to a multiple of 8 with zeros)."""
+    return ops.nchw_to_nhwc_bf16(x_nchw.contiguous().float())
+
+
+def dropout2d_nhwc(x, p, training):
+    """nn.Dropout2d on NHWC: one Bernoulli per (n, c) (model/pspnet.py:68,76)."""
+    if not training or p == 0.0:
+        return x
+    n, _, _, c = x.shape
+    keep = torch.empty((n, 1, 1, c), device=x.device, dtype=torch.float32).bernoulli_(1.0 - p)
+    return x * (keep / (1.0 - p)).to(x.dtype)
+
+
+def maxpool_nhwc(x, pool):
+    xn = x.permute(0, 3, 1, 2)
+    y = F.max_pool2d(xn, pool.kernel_size, pool.stride, pool.padding, pool.dilation, pool.ceil_mode)
+    return y.permute(0, 2, 3, 1).contiguous()

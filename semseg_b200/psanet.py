@@ -1,0 +1,192 @@
+"""PSANet, drop-in for the reference's model/psanet.py (same constructor / forward signatures, child module
+names, state_dict keys and return values — model/psanet.py:9-179), executed on NHWC bf16 activations.
+
+The point-wise spatial attention block keeps the reference's arithmetic order: reduce (1x1+BN+ReLU) ->
+bilinear shrink -> attention (1x1+BN+ReLU, 1x1) -> psa_mask collect/distribute -> softmax over the
+H*W source positions -> aggregation bmm -> proj -> bilinear upsample -> concat.
+"""
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from . import functional as SF
+from . import ops
+from . import resnet as models
+from .psa import psa_mask
+from .pspnet import head_forward_nhwc, upsample_logits
+
+
+def _interp_nhwc(x, size):
+    y = F.interpolate(x.permute(0, 3, 1, 2), size=size, mode='bilinear', align_corners=True)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+class PSA(nn.Module):
+    def __init__(self, in_channels=2048, mid_channels=512, psa_type=2, compact=False, shrink_factor=2, mask_h=59,
+                 mask_w=59, normalization_factor=1.0, psa_softmax=True):
+        super(PSA, self).__init__()
+        assert psa_type in [0, 1, 2]
+        self.psa_type = psa_type
+        self.compact = compact
+        self.shrink_factor = shrink_factor
+        self.mask_h = mask_h
+        self.mask_w = mask_w
+        self.psa_softmax = psa_softmax
+        if normalization_factor is None:
+            normalization_factor = mask_h * mask_w
+        self.normalization_factor = normalization_factor
+
+        self.reduce = nn.Sequential(
+            nn.Conv2d(in_channels, mid_channels, kernel_size=1, bias=False),
+            nn.BatchNorm2d(mid_channels),
+            nn.ReLU(inplace=True)
+        )
+        self.attention = nn.Sequential(
+            nn.Conv2d(mid_channels, mid_channels, kernel_size=1, bias=False),
+            nn.BatchNorm2d(mid_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(mid_channels, mask_h * mask_w, kernel_size=1, bias=False),
+        )
+        if psa_type == 2:
+            self.reduce_p = nn.Sequential(
+                nn.Conv2d(in_channels, mid_channels, kernel_size=1, bias=False),
+                nn.BatchNorm2d(mid_channels),
+                nn.ReLU(inplace=True)
+            )
+            self.attention_p = nn.Sequential(
+                nn.Conv2d(mid_channels, mid_channels, kernel_size=1, bias=False),
+                nn.BatchNorm2d(mid_channels),
+                nn.ReLU(inplace=True),
+                nn.Conv2d(mid_channels, mask_h * mask_w, kernel_size=1, bias=False),
+            )
+        self.proj = nn.Sequential(
+            nn.Conv2d(mid_channels * (2 if psa_type == 2 else 1), in_channels, kernel_size=1, bias=False),
+            nn.BatchNorm2d(in_channels),
+            nn.ReLU(inplace=True)
+        )
+
+    # ---- one attention branch -------------------------------------------------------------------------
+    def _branch(self, x, reduce, attention, mask_type):
+        """x NHWC bf16 [n,H,W,C] -> aggregated features NHWC bf16 [n,h,w,mid] at the shrunk resolution."""
+        t = SF.conv_bn_act(x, reduce[0], reduce[1], relu=True)
+        n, h, w, c = t.shape
+        if self.shrink_factor != 1:
+            h = (h - 1) // self.shrink_factor + 1
+            w = (w - 1) // self.shrink_factor + 1
+            t = _interp_nhwc(t, (h, w))
+        a = SF.conv_bn_act(t, attention[0], attention[1], relu=True)
+        y = SF.conv_bias_f32(a, attention[3])                 # fp32 NHWC [n,h,w,mask_h*mask_w]
+        y = y.permute(0, 3, 1, 2).contiguous()                # NCHW fp32, the layout psa_mask is defined on
+        if self.compact:
+            if mask_type == 1:
+                y = y.view(n, h * w, h * w).transpose(1, 2).reshape(n, h * w, h, w)
+        else:
+            y = psa_mask(y, mask_type, self.mask_h, self.mask_w)
+        if self.psa_softmax:
+            y = F.softmax(y, dim=1)
+        # reference: bmm(x[n,c,hw], y[n,hw,hw]) -> [n,c,hw]; in NHWC that is y^T @ x[n,hw,c]
+        agg = torch.bmm(y.view(n, h * w, h * w).transpose(1, 2), t.reshape(n, h * w, c).float())
+        agg = agg * (1.0 / self.normalization_factor)
+        return agg.to(torch.bfloat16).view(n, h, w, c), (h, w)
+
+    def forward_nhwc(self, x):
+        out = x
+        if self.psa_type in [0, 1]:
+            t, (h, w) = self._branch(x, self.reduce, self.attention, self.psa_type)
+        else:
+            t_col, (h, w) = self._branch(x, self.reduce, self.attention, 0)
+            t_dis, _ = self._branch(x, self.reduce_p, self.attention_p, 1)
+            t = torch.cat([t_col, t_dis], 3)
+        t = SF.conv_bn_act(t, self.proj[0], self.proj[1], relu=True)
+        if self.shrink_factor != 1:
+            h = (h - 1) * self.shrink_factor + 1
+            w = (w - 1) * self.shrink_factor + 1
+            t = _interp_nhwc(t, (h, w))
+        return torch.cat((out, t), 3)
+
+    def forward(self, x):
+        y = self.forward_nhwc(SF.to_nhwc_bf16(x))
+        return y.permute(0, 3, 1, 2).float()
+
+
+class PSANet(nn.Module):
+    def __init__(self, layers=50, dropout=0.1, classes=2, zoom_factor=8, use_psa=True, psa_type=2, compact=False,
+                 shrink_factor=2, mask_h=59, mask_w=59, normalization_factor=1.0, psa_softmax=True,
+                 criterion=nn.CrossEntropyLoss(ignore_index=255), pretrained=True):
+        super(PSANet, self).__init__()
+        assert layers in [50, 101, 152]
+        assert classes > 1
+        assert zoom_factor in [1, 2, 4, 8]
+        assert psa_type in [0, 1, 2]
+        self.zoom_factor = zoom_factor
+        self.use_psa = use_psa
+        self.criterion = criterion
+
+        if layers == 50:
+            resnet = models.resnet50(pretrained=pretrained)
+        elif layers == 101:
+            resnet = models.resnet101(pretrained=pretrained)
+        else:
+            resnet = models.resnet152(pretrained=pretrained)
+        self.layer0 = resnet.stem()
+        self.layer1, self.layer2, self.layer3, self.layer4 = resnet.layer1, resnet.layer2, resnet.layer3, resnet.layer4
+
+        for n, m in self.layer3.named_modules():
+            if 'conv2' in n:
+                m.dilation, m.padding, m.stride = (2, 2), (2, 2), (1, 1)
+            elif 'downsample.0' in n:
+                m.stride = (1, 1)
+        for n, m in self.layer4.named_modules():
+            if 'conv2' in n:
+                m.dilation, m.padding, m.stride = (4, 4), (4, 4), (1, 1)
+            elif 'downsample.0' in n:
+                m.stride = (1, 1)
+
+        fea_dim = 2048
+        if use_psa:
+            self.psa = PSA(fea_dim, 512, psa_type, compact, shrink_factor, mask_h, mask_w, normalization_factor,
+                           psa_softmax)
+            fea_dim *= 2
+        self.cls = nn.Sequential(
+            nn.Conv2d(fea_dim, 512, kernel_size=3, padding=1, bias=False),
+            nn.BatchNorm2d(512),
+            nn.ReLU(inplace=True),
+            nn.Dropout2d(p=dropout),
+            nn.Conv2d(512, classes, kernel_size=1)
+        )
+        if self.training:
+            self.aux = nn.Sequential(
+                nn.Conv2d(1024, 256, kernel_size=3, padding=1, bias=False),
+                nn.BatchNorm2d(256),
+                nn.ReLU(inplace=True),
+                nn.Dropout2d(p=dropout),
+                nn.Conv2d(256, classes, kernel_size=1)
+            )
+
+    def forward(self, x, y=None):
+        x_size = x.size()
+        assert (x_size[2] - 1) % 8 == 0 and (x_size[3] - 1) % 8 == 0
+        h = int((x_size[2] - 1) / 8 * self.zoom_factor + 1)
+        w = int((x_size[3] - 1) / 8 * self.zoom_factor + 1)
+
+        t = SF.to_nhwc_bf16(x)
+        t = self.layer0.forward_nhwc(t)
+        t = self.layer1.forward_nhwc(t)
+        t = self.layer2.forward_nhwc(t)
+        t_tmp = self.layer3.forward_nhwc(t)
+        t = self.layer4.forward_nhwc(t_tmp)
+        if self.use_psa:
+            t = self.psa.forward_nhwc(t)
+        logits = head_forward_nhwc(self.cls, t)
+
+        if self.training:
+            x = upsample_logits(logits, (h, w), self.zoom_factor)
+            aux = upsample_logits(head_forward_nhwc(self.aux, t_tmp), (h, w), self.zoom_factor)
+            main_loss = self.criterion(x, y)
+            aux_loss = self.criterion(aux, y)
+            return x.max(1)[1], main_loss, aux_loss
+        else:
+            x = ops.nhwc_f32_to_nchw(logits) if not logits.requires_grad else logits.permute(0, 3, 1, 2).contiguous()
+            if self.zoom_factor != 1:
+                x = F.interpolate(x, size=(h, w), mode='bilinear', align_corners=True)
+            return x

@@ -1,0 +1,140 @@
+"""PSPNet, drop-in for the reference's model/pspnet.py (same constructor / forward signatures, same child
+module names and state_dict keys, same return values — model/pspnet.py:29-105), executed on NHWC bf16
+activations by the sm_100a kernels behind semseg_b200/functional.py.
+"""
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from . import functional as SF
+from . import ops
+from . import resnet as models
+
+
+class PPM(nn.Module):
+    """Pyramid pooling module (model/pspnet.py:8-26): per bin AdaptiveAvgPool2d -> 1x1 conv -> BN -> ReLU ->
+    bilinear upsample (align_corners=True) -> concat with the input."""
+
+    def __init__(self, in_dim, reduction_dim, bins):
+        super(PPM, self).__init__()
+        self.features = []
+        for bin in bins:
+            self.features.append(nn.Sequential(
+                nn.AdaptiveAvgPool2d(bin),
+                nn.Conv2d(in_dim, reduction_dim, kernel_size=1, bias=False),
+                nn.BatchNorm2d(reduction_dim),
+                nn.ReLU(inplace=True)
+            ))
+        self.features = nn.ModuleList(self.features)
+
+    def forward_nhwc(self, x):
+        n, h, w, c = x.shape
+        xn = x.permute(0, 3, 1, 2)
+        out = [x]
+        for f in self.features:
+            p = F.adaptive_avg_pool2d(xn, f[0].output_size).permute(0, 2, 3, 1).contiguous()
+            y = SF.conv_bn_act(p, f[1], f[2], relu=True)
+            up = F.interpolate(y.permute(0, 3, 1, 2), (h, w), mode='bilinear', align_corners=True)
+            out.append(up.permute(0, 2, 3, 1))
+        return torch.cat(out, 3)
+
+    def forward(self, x):
+        y = self.forward_nhwc(SF.to_nhwc_bf16(x))
+        return y.permute(0, 3, 1, 2).float()
+
+
+def head_forward_nhwc(head, t):
+    """cls / aux head: 3x3 conv + BN + ReLU + Dropout2d + 1x1 conv with bias -> fp32 NHWC logits."""
+    t = SF.conv_bn_act(t, head[0], head[1], relu=True)
+    t = SF.dropout2d_nhwc(t, head[3].p, head[3].training)
+    return SF.conv_bias_f32(t, head[4])
+
+
+def upsample_logits(logits_nhwc, size, zoom_factor):
+    """fp32 NHWC logits -> NCHW (view) bilinearly upsampled to `size` (model/pspnet.py:94-95)."""
+    x = logits_nhwc.permute(0, 3, 1, 2)
+    if zoom_factor != 1:
+        x = F.interpolate(x, size=size, mode='bilinear', align_corners=True)
+    return x
+
+
+class PSPNet(nn.Module):
+    def __init__(self, layers=50, bins=(1, 2, 3, 6), dropout=0.1, classes=2, zoom_factor=8, use_ppm=True,
+                 criterion=nn.CrossEntropyLoss(ignore_index=255), pretrained=True):
+        super(PSPNet, self).__init__()
+        assert layers in [50, 101, 152]
+        assert 2048 % len(bins) == 0
+        assert classes > 1
+        assert zoom_factor in [1, 2, 4, 8]
+        self.zoom_factor = zoom_factor
+        self.use_ppm = use_ppm
+        self.criterion = criterion
+
+        if layers == 50:
+            resnet = models.resnet50(pretrained=pretrained)
+        elif layers == 101:
+            resnet = models.resnet101(pretrained=pretrained)
+        else:
+            resnet = models.resnet152(pretrained=pretrained)
+        self.layer0 = resnet.stem()
+        self.layer1, self.layer2, self.layer3, self.layer4 = resnet.layer1, resnet.layer2, resnet.layer3, resnet.layer4
+
+        # output stride 8: dilate layer3 / layer4 instead of striding (model/pspnet.py:49-58)
+        for n, m in self.layer3.named_modules():
+            if 'conv2' in n:
+                m.dilation, m.padding, m.stride = (2, 2), (2, 2), (1, 1)
+            elif 'downsample.0' in n:
+                m.stride = (1, 1)
+        for n, m in self.layer4.named_modules():
+            if 'conv2' in n:
+                m.dilation, m.padding, m.stride = (4, 4), (4, 4), (1, 1)
+            elif 'downsample.0' in n:
+                m.stride = (1, 1)
+
+        fea_dim = 2048
+        if use_ppm:
+            self.ppm = PPM(fea_dim, int(fea_dim / len(bins)), bins)
+            fea_dim *= 2
+        self.cls = nn.Sequential(
+            nn.Conv2d(fea_dim, 512, kernel_size=3, padding=1, bias=False),
+            nn.BatchNorm2d(512),
+            nn.ReLU(inplace=True),
+            nn.Dropout2d(p=dropout),
+            nn.Conv2d(512, classes, kernel_size=1)
+        )
+        if self.training:
+            self.aux = nn.Sequential(
+                nn.Conv2d(1024, 256, kernel_size=3, padding=1, bias=False),
+                nn.BatchNorm2d(256),
+                nn.ReLU(inplace=True),
+                nn.Dropout2d(p=dropout),
+                nn.Conv2d(256, classes, kernel_size=1)
+            )
+
+    def forward(self, x, y=None):
+        x_size = x.size()
+        assert (x_size[2] - 1) % 8 == 0 and (x_size[3] - 1) % 8 == 0
+        h = int((x_size[2] - 1) / 8 * self.zoom_factor + 1)
+        w = int((x_size[3] - 1) / 8 * self.zoom_factor + 1)
+
+        t = SF.to_nhwc_bf16(x)
+        t = self.layer0.forward_nhwc(t)
+        t = self.layer1.forward_nhwc(t)
+        t = self.layer2.forward_nhwc(t)
+        t_tmp = self.layer3.forward_nhwc(t)
+        t = self.layer4.forward_nhwc(t_tmp)
+        if self.use_ppm:
+            t = self.ppm.forward_nhwc(t)
+        logits = head_forward_nhwc(self.cls, t)
+
+        if self.training:
+            x = upsample_logits(logits, (h, w), self.zoom_factor)
+            aux = upsample_logits(head_forward_nhwc(self.aux, t_tmp), (h, w), self.zoom_factor)
+            main_loss = self.criterion(x, y)
+            aux_loss = self.criterion(aux, y)
+            return x.max(1)[1], main_loss, aux_loss
+        else:
+            x = ops.nhwc_f32_to_nchw(logits) if not logits.requires_grad else logits.permute(0, 3, 1, 2).contiguous()
+            if self.zoom_factor != 1:
+                x = F.interpolate(x, size=(h, w), mode='bilinear', align_corners=True)
+            return x

@@ -1,0 +1,55 @@
+"""CPU tier: the N>1 host path on gloo, world_size 2 — SyncBN statistics exchange/merge and bench timing
+reduction. (The kernels need a GPU; what is covered here is the rank plumbing around them.)"""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle.torch_oracle import merge_moments
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from semseg_b200.dist_utils import gather_rank_stats, max_over_ranks, shard_batch
+    try:
+        rng = np.random.default_rng(0)
+        full = (rng.standard_normal((8, 50, 16)) * 3 + 1.5).astype(np.float64)   # [images, pixels, C]
+        mine = full[list(shard_batch(8, world, rank))].reshape(-1, 16)
+        local = np.stack([mine.mean(0), ((mine - mine.mean(0)) ** 2).sum(0), np.full(16, mine.shape[0], float)])
+        g = gather_rank_stats(torch.from_numpy(local))
+        assert tuple(g.shape) == (world, 3, 16)
+        mean, m2, n = merge_moments([(g[r, 0].numpy(), g[r, 1].numpy(), g[r, 2].numpy()) for r in range(world)])
+        allx = full.reshape(-1, 16)
+        ok = np.allclose(mean, allx.mean(0), atol=1e-12) and np.allclose(m2 / n, allx.var(0), atol=1e-12)
+        ok = ok and bool((n == allx.shape[0]).all())
+        t = max_over_ranks(1.0 + rank, "cpu")
+        ok = ok and t == float(world)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_syncbn_stats_exchange_and_timing_reduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -1,0 +1,315 @@
+"""GPU tier (-m gpu): parity of the CUDA path, called through the C-ABI, against the oracle.
+
+  * psa_mask            : bit-exact vs the C oracle (oracle/psamask_oracle.c) and the committed reference goldens.
+  * conv / BN kernels   : vs a plain torch fp32 reference of the same op on bf16-rounded operands
+                          (tolerance = bf16 output rounding, 2^-8 relative, stated per test).
+  * blocks and networks : vs oracle/torch_oracle.py (fp32, TF32 off) on identical seeded weights and inputs.
+Tolerances for the bf16 tensor-core path are the measured single-pass bf16 floors of SURVEY.md §7 / BASELINE.md
+(per layer ~3e-3 rel-L2; losses to 2e-3; the network is chaotic in train mode, so logits are compared in eval).
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _strict_fp32():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+# ------------------------------------------------------------------------------------------------ psa_mask
+PSA_CASES = [(2, 4, 5, 7, 9), (1, 6, 7, 5, 3), (2, 5, 5, 9, 9), (1, 30, 30, 59, 59), (1, 1, 1, 1, 1),
+             (1, 3, 9, 5, 17), (2, 8, 8, 3, 3)]
+
+
+@pytest.mark.parametrize("case", PSA_CASES)
+@pytest.mark.parametrize("psa_type", [0, 1])
+def test_psamask_bit_exact_vs_oracle(case, psa_type):
+    from semseg_b200 import ops
+    n, h, w, mh, mw = case
+    rng = np.random.default_rng(hash(case) % 1000 + psa_type)
+    x = rng.standard_normal((n, mh * mw, h, w)).astype(np.float32)
+    g = rng.standard_normal((n, h * w, h, w)).astype(np.float32)
+    out = ops.psamask_fwd(torch.from_numpy(x).cuda(), psa_type, mh, mw).cpu().numpy()
+    din = ops.psamask_bwd(torch.from_numpy(g).cuda(), psa_type, mh, mw).cpu().numpy()
+    assert np.array_equal(out, oracle.psamask_fwd(x, psa_type, mh, mw))
+    assert np.array_equal(din, oracle.psamask_bwd(g, psa_type, mh, mw))
+
+
+def test_psamask_matches_reference_goldens(golden_dir):
+    from lib.psa.functional import psa_mask
+    g = np.load(os.path.join(golden_dir, "psamask.npz"))
+    rng = np.random.default_rng(7)
+    for (n, h, w, mh, mw) in [(2, 4, 5, 7, 9), (1, 6, 7, 5, 3), (2, 5, 5, 9, 9), (1, 30, 30, 59, 59)]:
+        for t in (0, 1):
+            key = "n%d_h%d_w%d_mh%d_mw%d_t%d" % (n, h, w, mh, mw, t)
+            x = rng.standard_normal((n, mh * mw, h, w)).astype(np.float32)
+            xt = torch.from_numpy(x).cuda().requires_grad_(True)
+            o = psa_mask(xt, t, mh, mw)
+            go = rng.standard_normal(tuple(o.shape)).astype(np.float32)
+            o.backward(torch.from_numpy(go).cuda())
+            assert hashlib.sha256(o.detach().cpu().numpy().tobytes()).hexdigest() == str(g[key + "/out_sha"])
+            assert hashlib.sha256(xt.grad.cpu().numpy().tobytes()).hexdigest() == str(g[key + "/din_sha"])
+
+
+def test_psamask_full_size_properties():
+    """BASELINE config-3 size (N=16 per GPU in the weak-scaling variant): round-trip / transpose properties."""
+    from semseg_b200 import ops
+    n, h, w = 16, 30, 30
+    x = torch.randn((n, 59 * 59, h, w), device="cuda")
+    col = ops.psamask_fwd(x, 0, 59, 59)
+    dis = ops.psamask_fwd(x, 1, 59, 59)
+    assert torch.equal(dis, col.view(n, 900, 900).transpose(1, 2).reshape(n, 900, h, w))
+    # bwd(fwd(x)) keeps exactly the entries that participate and zeroes the rest; applying it twice is idempotent
+    back = ops.psamask_bwd(col, 0, 59, 59)
+    mask = back != 0
+    assert torch.equal(back[mask], x[mask])
+    assert torch.equal(ops.psamask_bwd(ops.psamask_fwd(back, 0, 59, 59), 0, 59, 59), back)
+    frac = mask.float().mean().item()
+    assert abs(frac - (900.0 / 3481.0)) < 1e-3   # (HW)^2 of mH*mW*HW input elements are live (25.9 %)
+
+
+def test_psamask_rejects_bad_arguments():
+    from semseg_b200 import ops, _lib
+    with pytest.raises(_lib.SemsegError):
+        ops.psamask_fwd(torch.zeros(1, 16, 2, 2, device="cuda"), 0, 4, 4)   # even mask
+    with pytest.raises(RuntimeError):
+        from lib.psa.functional import psa_mask
+        psa_mask(torch.zeros(1, 9, 2, 2, device="cuda", dtype=torch.float64), 0, 3, 3)
+
+
+# ------------------------------------------------------------------------------------------------ conv kernels
+def _ref_conv(x_nhwc, w, dil):
+    k = w.shape[-1]
+    y = F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=dil * (k // 2),
+                 dilation=dil)
+    return y.permute(0, 2, 3, 1)
+
+
+CONV_CASES = [(1, 8, 16, 64, 64, 1, 1), (2, 12, 12, 64, 256, 1, 1), (2, 60, 60, 256, 256, 3, 2),
+              (2, 60, 60, 512, 512, 3, 4), (2, 60, 60, 512, 2048, 1, 1), (1, 119, 119, 64, 64, 3, 1),
+              (2, 59, 59, 256, 512, 3, 1), (1, 90, 90, 256, 256, 3, 2), (16, 1, 1, 2048, 512, 1, 1),
+              (2, 6, 6, 2048, 512, 1, 1), (1, 237, 237, 64, 128, 3, 1)]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fprop_dgrad_wgrad_vs_torch_fp32(case):
+    from semseg_b200 import ops
+    n, h, w, cin, cout, k, dil = case
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn((n, h, w, cin), device="cuda", generator=g).to(torch.bfloat16)
+    wt = torch.randn((cout, cin, k, k), device="cuda", generator=g) / (cin * k * k) ** 0.5
+    dy = torch.randn((n, h, w, cout), device="cuda", generator=g).to(torch.bfloat16)
+    pw = ops.pack_weights(wt)
+    y, sp, tc = ops.conv_fprop(x, pw.wf, cout, ops.conv_taps(k, dil), stats=True)
+    xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wf = wt.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv2d(xf, wf, padding=dil * (k // 2), dilation=dil)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    # bf16 output rounding: |err| <= 2^-9 |y| per element; fp32 accumulation order differs
+    assert util.rel_l2(y, ref.permute(0, 2, 3, 1)) < 3e-3
+    st = ops.bn_merge_partials(sp, tc)
+    yf = y.float().reshape(-1, cout)
+    assert torch.allclose(st[0], yf.mean(0), atol=1e-4)
+    assert torch.allclose(st[1] / st[2], yf.var(0, unbiased=False), rtol=1e-3, atol=1e-6)
+    assert bool((st[2] == yf.shape[0]).all())
+    dx, _, _ = ops.conv_fprop(dy, pw.wd, cin, ops.conv_taps(k, dil, transpose=True))
+    assert util.rel_l2(dx, xf.grad.permute(0, 2, 3, 1)) < 3e-3
+    dw = ops.conv_wgrad(x, dy, cin, cout, ops.conv_taps(k, dil))
+    assert util.rel_l2(dw, wf.grad) < 1e-4      # fp32 output, only summation order differs
+
+
+def test_conv_linearity_full_size():
+    """Config-2 size (bs16, 60x60, layer4 3x3 d4): conv(a + b) == conv(a) + conv(b) up to bf16 rounding."""
+    from semseg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn((16, 60, 60, 512), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn((16, 60, 60, 512), device="cuda", generator=g).to(torch.bfloat16)
+    wt = torch.randn((512, 512, 3, 3), device="cuda", generator=g) * 0.02
+    pw = ops.pack_weights(wt)
+    taps = ops.conv_taps(3, 4)
+    s = (a.float() + b.float()).to(torch.bfloat16)
+    ya, _, _ = ops.conv_fprop(a, pw.wf, 512, taps)
+    yb, _, _ = ops.conv_fprop(b, pw.wf, 512, taps)
+    ys, _, _ = ops.conv_fprop(s, pw.wf, 512, taps)
+    assert util.rel_l2(ys, ya.float() + yb.float()) < 6e-3
+    z, _, _ = ops.conv_fprop(torch.zeros_like(a), pw.wf, 512, taps)
+    assert float(z.float().abs().max()) == 0.0
+
+
+def test_conv_epilogues():
+    from semseg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n, h, w, cin, cout = 2, 30, 30, 128, 256
+    x = torch.randn((n, h, w, cin), device="cuda", generator=g).to(torch.bfloat16)
+    wt = torch.randn((cout, cin, 3, 3), device="cuda", generator=g) * 0.03
+    res = torch.randn((n, h, w, cout), device="cuda", generator=g).to(torch.bfloat16)
+    scale = torch.rand((cout,), device="cuda", generator=g) + 0.5
+    shift = torch.randn((cout,), device="cuda", generator=g)
+    pw = ops.pack_weights(wt)
+    y, _, _ = ops.conv_fprop(x, pw.wf, cout, ops.conv_taps(3, 1), epi=ops.EPI_AFFINE, relu=True, scale=scale,
+                             shift=shift, residual=res)
+    ref = torch.relu(_ref_conv(x, wt, 1) * scale + shift + res.float())
+    assert util.rel_l2(y, ref) < 3e-3
+    w2 = torch.randn((150, cin, 1, 1), device="cuda", generator=g) * 0.05
+    b2 = torch.randn((150,), device="cuda", generator=g)
+    y2, _, _ = ops.conv_fprop(x, ops.pack_weights(w2).wf, 150, ops.conv_taps(1, 1), epi=ops.EPI_F32, shift=b2)
+    assert util.rel_l2(y2, _ref_conv(x, w2, 1) + b2) < 1e-5    # fp32 epilogue: only accumulation order
+    buf = torch.zeros((n, h, w, 512), device="cuda", dtype=torch.bfloat16)
+    ops.conv_fprop(x, pw.wf, cout, ops.conv_taps(3, 1), out=buf[..., 256:512])
+    assert util.rel_l2(buf[..., 256:512], _ref_conv(x, wt, 1)) < 3e-3
+    assert bool((buf[..., :256] == 0).all())
+
+
+def test_bn_kernels_vs_torch():
+    from semseg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, h, w, c = 2, 30, 30, 256
+    x = (torch.randn((n, h, w, c), device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
+    gamma = torch.rand((c,), device="cuda", generator=g) + 0.5
+    beta = torch.randn((c,), device="cuda", generator=g)
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    mi, ss = ops.bn_finalize(ops.bn_stats(x), gamma, beta, 1e-5, 0.1, rm, rv)
+    res = torch.randn((n, h, w, c), device="cuda", generator=g).to(torch.bfloat16)
+    y = ops.bn_apply(x, ss, residual=res, relu=True)
+    xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    rf = res.float().permute(0, 3, 1, 2).requires_grad_(True)
+    pre = F.batch_norm(xf, rm2, rv2, gm, bt, True, 0.1, 1e-5) + rf
+    assert util.rel_l2(y, torch.relu(pre).permute(0, 2, 3, 1)) < 3e-3
+    assert torch.allclose(rm, rm2, atol=1e-6) and torch.allclose(rv, rv2, rtol=1e-5)
+    dy = torch.randn((n, h, w, c), device="cuda", generator=g).to(torch.bfloat16)
+    mask = (y.float() > 0).permute(0, 3, 1, 2)
+    (pre * mask * dy.float().permute(0, 3, 1, 2)).sum().backward()
+    sums = ops.bn_bwd_reduce(dy, y, x, mi, True)
+    dx, dres, dgb = ops.bn_bwd_apply(dy, y, x, mi, gamma, sums, float(n * h * w), True, want_dres=True)
+    assert util.rel_l2(dx, xf.grad.permute(0, 2, 3, 1)) < 3e-3
+    assert util.rel_l2(dres, rf.grad.permute(0, 2, 3, 1)) < 1e-6
+    assert util.rel_l2(dgb[0], gm.grad) < 1e-5 and util.rel_l2(dgb[1], bt.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ blocks
+def _grad_check(model_params, oracle_sd, names, tol):
+    bad = []
+    for k in names:
+        e = util.rel_l2(model_params[k].grad, oracle_sd[k].grad)
+        if not e < tol:
+            bad.append((k, e))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("dil,planes", [(2, 256), (4, 512)])
+def test_bottleneck_block_vs_oracle(dil, planes):
+    """The named kernel path: 1x1 -> dilated 3x3 -> 1x1 + BN/ReLU/residual, forward and gradients."""
+    from semseg_b200.resnet import Bottleneck
+    from oracle.torch_oracle import Oracle
+    torch.manual_seed(0)
+    blk = Bottleneck(planes * 4, planes).cuda()
+    blk.conv2.dilation, blk.conv2.padding = (dil, dil), (dil, dil)
+    for m in blk.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            torch.nn.init.uniform_(m.weight, 0.5, 1.5)
+            torch.nn.init.normal_(m.bias, 0, 0.2)
+    x = torch.randn((2, planes * 4, 30, 30), device="cuda")
+    xb = x.to(torch.bfloat16).float()            # both sides see the same bf16-representable input
+    sd = {"layer1.0." + k: v.detach().clone() for k, v in blk.state_dict().items()}
+    for k, v in sd.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
+    orc = Oracle(sd)
+    xo = xb.clone().requires_grad_(True)
+    yo = orc.bottleneck(xo, "layer1.0", 1, dil, False)
+    from semseg_b200 import functional as SF
+    xi = SF.to_nhwc_bf16(xb).requires_grad_(True)
+    yi = blk.forward_nhwc(xi)
+    assert util.rel_l2(yi.permute(0, 3, 1, 2), yo) < 8e-3
+    go = torch.randn_like(yo)
+    yo.backward(go)
+    yi.backward(go.permute(0, 2, 3, 1).to(torch.bfloat16))
+    assert util.rel_l2(xi.grad.permute(0, 3, 1, 2), xo.grad) < 2e-2
+    params = dict(blk.named_parameters())
+    for k, p in params.items():
+        assert util.rel_l2(p.grad, sd["layer1.0." + k].grad) < 2e-2, k
+
+
+def _run_net(arch, size, classes, n, eval_tol, loss_tol):
+    build = util.build_pspnet if arch == "psp" else util.build_psanet
+    okw = {} if arch == "psp" else dict(mask_h=2 * ((size - 1) // 16 + 1) - 1, mask_w=2 * ((size - 1) // 16 + 1) - 1)
+    bkw = {} if arch == "psp" else dict(mask=okw["mask_h"])
+    model = build(50, classes, **bkw).cuda()
+    orc, sd = util.oracle_from(model, arch, layers=50, classes=classes, **okw)
+    x, y = util.synth(n, size, size, classes, device="cuda")
+    # eval on the freshly constructed model (the well-conditioned regime)
+    model.eval()
+    orc.eval()
+    with torch.no_grad():
+        lo = orc.forward(x)
+        lm = model(x)
+    e = util.rel_l2(lm, lo)
+    flips = (lm.argmax(1) != lo.argmax(1)).float().mean().item()
+    # train step: losses and gradients
+    model.train()
+    orc.train()
+    out, ml, al = model(x, y)
+    (ml + 0.4 * al).backward()
+    oo, mlo, alo = orc.forward(x, y)
+    (mlo + 0.4 * alo).backward()
+    return dict(eval_rel_l2=e, eval_flips=flips, main=(ml.item(), mlo.item()), aux=(al.item(), alo.item()),
+                model=model, sd=sd, out=out, oo=oo)
+
+
+def test_pspnet50_small_vs_oracle_and_reference_golden(golden_dir):
+    r = _run_net("psp", 65, 150, 2, None, None)
+    assert r["eval_rel_l2"] < 2e-2, r["eval_rel_l2"]          # single-pass bf16 floor is ~1e-2
+    assert r["eval_flips"] < 0.05
+    assert abs(r["main"][0] - r["main"][1]) < 2e-3 * r["main"][1]
+    assert abs(r["aux"][0] - r["aux"][1]) < 2e-3 * r["aux"][1]
+    g = np.load(os.path.join(golden_dir, "pspnet50_65.npz"))
+    assert abs(r["main"][0] - float(g["main_loss"])) < 2e-3 * float(g["main_loss"])
+    assert abs(r["aux"][0] - float(g["aux_loss"])) < 2e-3 * float(g["aux_loss"])
+    params = dict(r["model"].named_parameters())
+    for k in ("cls.4.weight", "cls.4.bias", "aux.4.bias", "cls.0.weight", "ppm.features.3.1.weight"):
+        assert util.rel_l2(params[k].grad, r["sd"][k].grad) < 5e-2, k
+
+
+def test_psanet50_small_vs_oracle():
+    r = _run_net("psa", 65, 150, 2, None, None)
+    assert r["eval_rel_l2"] < 2e-2, r["eval_rel_l2"]
+    assert abs(r["main"][0] - r["main"][1]) < 2e-3 * r["main"][1]
+    assert abs(r["aux"][0] - r["aux"][1]) < 2e-3 * r["aux"][1]
+    params = dict(r["model"].named_parameters())
+    for k in ("cls.4.bias", "psa.proj.0.weight", "psa.attention.3.weight"):
+        assert util.rel_l2(params[k].grad, r["sd"][k].grad) < 5e-2, k
+
+
+def test_pspnet50_config2_shape_train_step_loss_parity():
+    """BASELINE config 2 shape at a batch the fp32 oracle fits quickly: 473x473, 150 classes."""
+    r = _run_net("psp", 473, 150, 2, None, None)
+    assert r["eval_rel_l2"] < 2e-2, r["eval_rel_l2"]
+    assert abs(r["main"][0] - r["main"][1]) < 2e-3 * r["main"][1]
+    assert abs(r["aux"][0] - r["aux"][1]) < 2e-3 * r["aux"][1]
+    assert tuple(r["out"].shape) == (2, 473, 473) and r["out"].dtype == torch.int64
+
+
+def test_state_dict_round_trip_with_oracle_weights():
+    m = util.build_pspnet(50, 21).cuda()
+    sd = m.state_dict()
+    m2 = util.build_pspnet(50, 21, seed=5).cuda()
+    m2.load_state_dict(sd)
+    x, _ = util.synth(2, 65, 65, 21, device="cuda")
+    m.eval(), m2.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x), m2(x))        # deterministic kernels: same weights, same bits
