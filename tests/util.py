@@ -13,8 +13,8 @@ def synth(n, h, w, classes, seed=123, device="cpu"):
 
 
 def rel_l2(a, b):
-    a = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).double().flatten().cpu()
-    b = torch.as_tensor(np.asarray(b) if not torch.is_tensor(b) else b).double().flatten().cpu()
+    a = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a.detach()).double().flatten().cpu()
+    b = torch.as_tensor(np.asarray(b) if not torch.is_tensor(b) else b.detach()).double().flatten().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
