@@ -163,6 +163,11 @@ long long semseg_bn_workspace_floats(int M, int C);
 int semseg_bn_finalize(const float* rank_stats, int R, int C, const float* gamma, const float* beta, float eps,
                        float momentum, float* running_mean, float* running_var, float* mean_invstd,
                        float* scale_shift, void* stream);
+/* Single-rank fast path: semseg_bn_merge_partials + semseg_bn_finalize (R = 1) in one launch. */
+int semseg_bn_finalize_partials(const float* stats_partial, const float* tile_count, int num_tiles, int C,
+                                const float* gamma, const float* beta, float eps, float momentum,
+                                float* running_mean, float* running_var, float* mean_invstd, float* scale_shift,
+                                void* stream);
 /* Eval-mode folding: scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
 int semseg_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, int C, float* scale_shift, void* stream);
@@ -187,6 +192,41 @@ int semseg_relu_bwd(const void* dy, int dy_pitch, const void* y, int y_pitch, vo
 /* out = a + b (bf16 NHWC, used to merge gradient branches). */
 int semseg_add_bf16(const void* a, int a_pitch, const void* b, int b_pitch, void* out, int out_pitch, int M,
                     int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pyramid pooling module data movement (model/pspnet.py:12-26), NHWC bf16, all bins in one launch.
+ *   bins[nb] = pooled sizes (1,2,3,6); per-bin tensors are [N][b][b][channels] contiguous bf16.
+ *   ppm_pool            : pooled_k = AdaptiveAvgPool2d(b_k)(x), window [floor(i*H/b), ceil((i+1)*H/b)).
+ *   ppm_pool_bwd        : dx (dense, every element written) = sum_k adjoint of the pooling applied to dpooled_k.
+ *   ppm_upsample_concat : out[..., 0:C] = x; out[..., C + k*Cr : C + (k+1)*Cr] = bilinear(align_corners=True) of
+ *                         feats_k to H x W (the torch.cat of model/pspnet.py:26 written in place).
+ *   ppm_upsample_bwd    : dfeats_k = adjoint of the bilinear upsample applied to dout[..., c_off + k*Cr : ...].
+ */
+int semseg_ppm_pool(const void* x, int x_pitch, int N, int H, int W, int C, const int* bins, void* const* pooled,
+                    int nb, void* stream);
+int semseg_ppm_pool_bwd(void* const* dpooled, const int* bins, int nb, int N, int H, int W, int C, void* dx,
+                        int dx_pitch, void* stream);
+int semseg_ppm_upsample_concat(const void* x, int x_pitch, void* const* feats, const int* bins, int nb, int N, int H,
+                               int W, int C, int Cr, void* out, int out_pitch, void* stream);
+int semseg_ppm_upsample_bwd(const void* dout, int dout_pitch, int c_off, void* const* dfeats, const int* bins, int nb,
+                            int N, int H, int W, int Cr, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused logit upsample (bilinear, align_corners=True, x8) + cross-entropy (ignore_index, mean over valid
+ * pixels) + argmax: F.interpolate + CrossEntropyLoss + max(1) of model/pspnet.py:94-103 without the
+ * [N, classes, Ho, Wo] tensor. Requires Ho = 8(h-1)+1, Wo = 8(w-1)+1 (zoom_factor 8), classes <= 256.
+ *   logits fp32 NHWC [N,h,w,C] (pitch), target int64 [N,Ho,Wo].
+ *   fwd: loss_out[0] = mean CE, loss_out[1] = number of non-ignored pixels; argmax int64 [N,Ho,Wo] (or NULL);
+ *        lse fp32 [N,Ho,Wo] (saved for backward); workspace: semseg_upsample_ce_workspace_floats() floats.
+ *   bwd: dlogits fp32 [N,h,w,C] (dense, every element written) = grad_out[0] * d(mean CE)/dlogits.
+ */
+long long semseg_upsample_ce_workspace_floats(int N, int Ho, int Wo);
+int semseg_upsample_ce_fwd(const float* logits, int pitch, int N, int h, int w, int C, const int64_t* target,
+                           int Ho, int Wo, int ignore_index, float* workspace, float* loss_out, int64_t* argmax,
+                           float* lse, void* stream);
+int semseg_upsample_ce_bwd(const float* logits, int pitch, int N, int h, int w, int C, const int64_t* target,
+                           int Ho, int Wo, int ignore_index, const float* lse, const float* loss_info,
+                           const float* grad_out, float* dlogits, void* stream);
 
 #ifdef __cplusplus
 }

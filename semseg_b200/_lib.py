@@ -78,6 +78,8 @@ SIGNATURES = {
     "semseg_bn_stats": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_ll, c_vp, c_vp]),
     "semseg_bn_workspace_floats": (c_ll, [c_int, c_int]),
     "semseg_bn_finalize": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "semseg_bn_finalize_partials": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp,
+                                            c_vp]),
     "semseg_bn_fold_eval": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_vp, c_vp]),
     "semseg_bn_apply": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_bn_bwd_reduce": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp, c_ll,
@@ -86,6 +88,16 @@ SIGNATURES = {
                                     c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     "semseg_relu_bwd": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp]),
     "semseg_add_bf16": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp]),
+    "semseg_ppm_pool": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    "semseg_ppm_pool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "semseg_ppm_upsample_concat": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
+                                           c_int, c_vp]),
+    "semseg_ppm_upsample_bwd": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_upsample_ce_workspace_floats": (c_ll, [c_int, c_int, c_int]),
+    "semseg_upsample_ce_fwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp,
+                                       c_vp, c_vp, c_vp, c_vp]),
+    "semseg_upsample_ce_bwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp,
+                                       c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

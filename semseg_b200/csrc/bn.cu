@@ -56,6 +56,50 @@ __global__ void bn_merge_partials_kernel(const float* __restrict__ part, const f
 }
 
 // ------------------------------------------------------------------------------------------------
+// Single-rank fast path: merge the per-tile partials AND finalise in one launch (no SyncBN exchange needed).
+__global__ void bn_finalize_partials_kernel(const float* __restrict__ part, const float* __restrict__ cnt, int T,
+                                            int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            float eps, float momentum, float* __restrict__ running_mean,
+                                            float* __restrict__ running_var, float* __restrict__ mean_invstd,
+                                            float* __restrict__ scale_shift) {
+  __shared__ Moments sm[32][33];
+  const int cl = threadIdx.x & 31;
+  const int tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  Moments acc = {0.f, 0.f, 0.f};
+  if (c < C) {
+    for (int t = tl; t < T; t += 32) {
+      const float n = cnt[t];
+      if (n > 0.f) {
+        Moments m;
+        m.n = n;
+        m.mean = part[(static_cast<size_t>(t) * 2) * C + c] / n;
+        m.m2 = part[(static_cast<size_t>(t) * 2 + 1) * C + c];
+        acc = merge(acc, m);
+      }
+    }
+  }
+  sm[tl][cl] = acc;
+  __syncthreads();
+  if (tl == 0 && c < C) {
+    Moments r = sm[0][cl];
+    for (int i = 1; i < 32; ++i) r = merge(r, sm[i][cl]);
+    const float var = r.n > 0.f ? r.m2 / r.n : 0.f;
+    const float invstd = rsqrtf(var + eps);
+    mean_invstd[c] = r.mean;
+    mean_invstd[C + c] = invstd;
+    const float sc = (gamma ? gamma[c] : 1.f) * invstd;
+    scale_shift[c] = sc;
+    scale_shift[C + c] = (beta ? beta[c] : 0.f) - r.mean * sc;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * r.mean;
+    if (running_var) {
+      const float unb = r.n > 1.f ? r.m2 / (r.n - 1.f) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic per-chunk statistics of x [M][pitch] (bf16): chunk = rows_per_chunk pixels.
 // block = 8 channel-groups (8 ch each = 64 channels) x 32 pixel lanes; grid = (C/64 ceil, chunks).
 __global__ void bn_chunk_stats_kernel(const __nv_bfloat16* __restrict__ x, int M, int C, int pitch,
@@ -188,22 +232,26 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return o;
 }
 
+// Grid sizing guarantees (gridDim.x * blockDim.x) % (C/8) == 0, so a thread keeps the same 8 channels for its
+// whole grid-stride loop and the per-channel coefficients are loaded once.
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, const float* __restrict__ ss,
                                 const __nv_bfloat16* __restrict__ res, int res_pitch, __nv_bfloat16* __restrict__ y,
                                 int y_pitch, long long M, int C, int relu) {
   const int groups = C >> 3;
   const long long total = M * groups;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+  long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int c0 = static_cast<int>(idx % groups) << 3;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    sc[q] = ss[c0 + q];
+    sh[q] = ss[C + c0 + q];
+  }
+  for (; idx < total; idx += stride) {
     const long long p = idx / groups;
-    const int c0 = static_cast<int>(idx - p * groups) << 3;
     float f[8];
     unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), f);
-    const float4 s0 = *reinterpret_cast<const float4*>(ss + c0), s1 = *reinterpret_cast<const float4*>(ss + c0 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(ss + C + c0),
-                 h1 = *reinterpret_cast<const float4*>(ss + C + c0 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
     float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (res) unpack8(*reinterpret_cast<const uint4*>(res + p * res_pitch + c0), r);
 #pragma unroll
@@ -311,10 +359,22 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
       dgamma_dbeta[C + c] = sums[c];
     }
   }
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+  long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int c0 = static_cast<int>(idx % groups) << 3;
+  // dx = g*invstd*(dz - s1/M - xhat*s2/M) = ka*dz + kx*x + kb  with xhat = (x - mean)*invstd
+  float ka[8], kx[8], kb[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = c0 + q;
+    const float mean = mean_invstd[c], invstd = mean_invstd[C + c];
+    const float g = gamma ? gamma[c] : 1.f;
+    ka[q] = g * invstd;
+    kx[q] = -ka[q] * invstd * sums[C + c] * inv_count;
+    kb[q] = -ka[q] * sums[c] * inv_count - kx[q] * mean;
+  }
+  for (; idx < total; idx += stride) {
     const long long p = idx / groups;
-    const int c0 = static_cast<int>(idx - p * groups) << 3;
     float d[8], xv[8];
     unpack8(*reinterpret_cast<const uint4*>(dy + p * dy_pitch + c0), d);
     unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), xv);
@@ -328,13 +388,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
     if (dres) *reinterpret_cast<uint4*>(dres + p * dres_pitch + c0) = pack8(d);
     float o[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int c = c0 + q;
-      const float mean = mean_invstd[c], invstd = mean_invstd[C + c];
-      const float g = gamma ? gamma[c] : 1.f;
-      const float xhat = (xv[q] - mean) * invstd;
-      o[q] = g * invstd * (d[q] - sums[c] * inv_count - xhat * sums[C + c] * inv_count);
-    }
+    for (int q = 0; q < 8; ++q) o[q] = fmaf(ka[q], d[q], fmaf(kx[q], xv[q], kb[q]));
     *reinterpret_cast<uint4*>(dx + p * dx_pitch + c0) = pack8(o);
   }
 }
@@ -383,6 +437,16 @@ static int ew_grid(long long total, int threads) {
   return static_cast<int>(b);
 }
 
+// Grid whose total thread count is a multiple of `groups` (= C/8), so each thread owns fixed channels.
+static int ew_grid_fixed_channels(long long total, int threads, int groups) {
+  long long b = ew_grid(total, threads);
+  // smallest m with (m * threads) % groups == 0
+  long long m = 1;
+  while ((m * threads) % groups != 0) ++m;
+  b = (b + m - 1) / m * m;
+  return static_cast<int>(b);
+}
+
 static int chunk_rows(int M) {
   int rows = cdiv(M, 1024);
   if (rows < 256) rows = 256;
@@ -406,6 +470,20 @@ extern "C" int semseg_bn_merge_partials(const float* stats_partial, const float*
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(stats_partial && tile_count && out_stats && num_tiles > 0 && C > 0, "bn_merge_partials: bad args");
   bn_merge_partials_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, tile_count, num_tiles, C, out_stats);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_bn_finalize_partials(const float* stats_partial, const float* tile_count, int num_tiles, int C,
+                                           const float* gamma, const float* beta, float eps, float momentum,
+                                           float* running_mean, float* running_var, float* mean_invstd,
+                                           float* scale_shift, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(stats_partial && tile_count && mean_invstd && scale_shift && num_tiles > 0 && C > 0,
+               "bn_finalize_partials: bad args");
+  bn_finalize_partials_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, tile_count, num_tiles, C, gamma, beta,
+                                                               eps, momentum, running_mean, running_var, mean_invstd,
+                                                               scale_shift);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
@@ -455,7 +533,7 @@ extern "C" int semseg_bn_apply(const void* x, int x_pitch, const float* scale_sh
   SB_CHECK_ARG(C % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && (!residual || res_pitch % 8 == 0),
                "bn_apply: channels and pitches must be multiples of 8");
   const long long total = static_cast<long long>(M) * (C / 8);
-  bn_apply_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_pitch, scale_shift,
+  bn_apply_kernel<<<ew_grid_fixed_channels(total, 256, C / 8), 256, 0, stream>>>(static_cast<const bf16*>(x), x_pitch, scale_shift,
                                                            static_cast<const bf16*>(residual), res_pitch,
                                                            static_cast<bf16*>(y), y_pitch, M, C, relu);
   SB_LAUNCHED();
@@ -494,7 +572,7 @@ extern "C" int semseg_bn_bwd_apply(const void* dy, int dy_pitch, const void* y, 
                    (!relu || y_pitch % 8 == 0) && (!dres || dres_pitch % 8 == 0),
                "bn_bwd_apply: channels and pitches must be multiples of 8");
   const long long total = static_cast<long long>(M) * (C / 8);
-  bn_bwd_apply_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(
+  bn_bwd_apply_kernel<<<ew_grid_fixed_channels(total, 256, C / 8), 256, 0, stream>>>(
       static_cast<const bf16*>(dy), dy_pitch, static_cast<const bf16*>(y), y_pitch, static_cast<const bf16*>(x),
       x_pitch, mean_invstd, gamma, sums, 1.f / count, M, C, relu, static_cast<bf16*>(dx), dx_pitch,
       static_cast<bf16*>(dres), dres_pitch, dgamma_dbeta);

@@ -75,7 +75,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint32_t* row_mask = tmem_ptr + 1;                                // [4] valid-row bits per 32-row group
-  float* stat_scratch = reinterpret_cast<float*>(misc + 512);       // [2 halves][64 cols][3]
+  float* stat_scratch = reinterpret_cast<float*>(misc + 512);       // [3 row quarters][32 column pairs][4] = 1536 B
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,8 +177,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int g = warp & 3;             // TMEM lane group this warp may access
     const int row = g * 32 + lane;      // accumulator row == pixel within the tile
     const int et = (warp - 2) * 32 + lane;  // 0..127
-    const int scol = et & 63;           // statistics: column within the 64-wide chunk
-    const int shalf = et >> 6;          // statistics: which 64-row half
     int tile_iter = 0;
     int store_buf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
@@ -282,57 +280,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
 
         if (p.stats_partial != nullptr && p.epi_mode == SEMSEG_EPI_RAW) {
-          // Per-column statistics of the bf16 values just staged (what BN-apply will read back).
-          // Each thread: one column, 64 rows; the two halves are merged with Chan's formula.
-          const int rbase = shalf * 64;
-          const uint32_t m_lo = row_mask[shalf * 2], m_hi = row_mask[shalf * 2 + 1];
-          float s = 0.f;
-          int cnt = 0;
-          const uint8_t* colp = obuf + (scol & 7) * 2;
-          const int chunk16 = scol >> 3;
-#pragma unroll 8
-          for (int r = 0; r < 64; ++r) {
-            const uint32_t bit = (r < 32) ? ((m_lo >> r) & 1u) : ((m_hi >> (r - 32)) & 1u);
-            const int rr = rbase + r;
-            const float x = __bfloat162float(
-                *reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + ((chunk16 ^ (rr & 7)) << 4)));
-            if (bit) {
-              s += x;
-              ++cnt;
+          // Per-column statistics of the bf16 values just staged (exactly what BN-apply will read back).
+          // Thread -> column pair cp (2 adjacent bf16 = one 4-byte word, conflict-free across the warp) and a
+          // quarter of the rows; one pass accumulates sum and sum of squares, the four quarters are combined in
+          // a fixed order and converted to (sum, M2 about the tile mean).
+          const int cp = et & 31;
+          const int rq = et >> 5;
+          const uint32_t msk = row_mask[rq];
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const uint8_t* base = obuf + (cp & 3) * 4;
+          const int chunk16 = cp >> 2;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const int rr = rq * 32 + r;
+            if ((msk >> r) & 1u) {
+              const __nv_bfloat162 v =
+                  *reinterpret_cast<const __nv_bfloat162*>(base + rr * 128 + ((chunk16 ^ (rr & 7)) << 4));
+              const float2 f = __bfloat1622float2(v);
+              s0 += f.x;
+              s1 += f.y;
+              q0 = fmaf(f.x, f.x, q0);
+              q1 = fmaf(f.y, f.y, q1);
             }
           }
-          const float mean_h = cnt > 0 ? s / static_cast<float>(cnt) : 0.f;
-          float m2 = 0.f;
-#pragma unroll 8
-          for (int r = 0; r < 64; ++r) {
-            const uint32_t bit = (r < 32) ? ((m_lo >> r) & 1u) : ((m_hi >> (r - 32)) & 1u);
-            const int rr = rbase + r;
-            const float x = __bfloat162float(
-                *reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + ((chunk16 ^ (rr & 7)) << 4)));
-            if (bit) {
-              const float d = x - mean_h;
-              m2 = fmaf(d, d, m2);
-            }
+          if (rq > 0) {  // quarters 1..3 publish to scratch ([3][32][4] floats = 1536 B); quarter 0 combines
+            float* sc = stat_scratch + ((rq - 1) * 32 + cp) * 4;
+            sc[0] = s0;
+            sc[1] = s1;
+            sc[2] = q0;
+            sc[3] = q1;
           }
-          float* sc = stat_scratch + (shalf * 64 + scol) * 3;
-          sc[0] = s;
-          sc[1] = m2;
-          sc[2] = static_cast<float>(cnt);
           named_bar_sync(2, kEpiThreads);
-          if (shalf == 0) {
-            const float* o = stat_scratch + (64 + scol) * 3;
-            const float s1 = o[0], m21 = o[1], n1 = o[2];
-            const float n0f = static_cast<float>(cnt);
-            const float nt = n0f + n1;
-            float tot_m2 = m2 + m21;
-            if (n0f > 0.f && n1 > 0.f) {
-              const float dlt = s1 / n1 - mean_h;
-              tot_m2 += dlt * dlt * n0f * n1 / nt;
+          if (rq == 0) {
+            float S0 = s0, S1 = s1, Q0 = q0, Q1 = q1;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const float* o = stat_scratch + (k * 32 + cp) * 4;
+              S0 += o[0];
+              S1 += o[1];
+              Q0 += o[2];
+              Q1 += o[3];
             }
+            const float nt = static_cast<float>(__popc(row_mask[0]) + __popc(row_mask[1]) + __popc(row_mask[2]) +
+                                                __popc(row_mask[3]));
+            const float inv = nt > 0.f ? 1.f / nt : 0.f;
             float* dst = p.stats_partial + static_cast<size_t>(m_tile) * 2 * p.Cout;
-            dst[c0 + scol] = s + s1;
-            dst[p.Cout + c0 + scol] = tot_m2;
-            if (n_tile == 0 && ch == 0 && scol == 0 && p.tile_count) p.tile_count[m_tile] = nt;
+            const int col = c0 + 2 * cp;
+            dst[col] = S0;
+            dst[col + 1] = S1;
+            dst[p.Cout + col] = fmaxf(Q0 - S0 * S0 * inv, 0.f);
+            dst[p.Cout + col + 1] = fmaxf(Q1 - S1 * S1 * inv, 0.f);
+            if (n_tile == 0 && ch == 0 && cp == 0 && p.tile_count) p.tile_count[m_tile] = nt;
           }
           named_bar_sync(2, kEpiThreads);  // scratch may be rewritten by the next chunk
         }

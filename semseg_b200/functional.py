@@ -88,9 +88,17 @@ class _ConvBnAct(torch.autograd.Function):
         pw = packed(conv)
         k, dil = conv.kernel_size[0], conv.dilation[0]
         raw, sp, tc = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(k, dil), stats=True)
-        stats = ops.bn_merge_partials(sp, tc)
         pg = _sync_group(bn)
-        mi, ss, world = _finalize_stats(stats, bn, pg)
+        if pg is None:
+            # single rank: merge the per-tile partials and finalise in one launch
+            track = bn.track_running_stats and bn.running_mean is not None
+            mi, ss = ops.bn_finalize_partials(sp, tc, bn.weight, bn.bias, bn.eps, _bn_momentum(bn) if track else 0.0,
+                                              bn.running_mean if track else None, bn.running_var if track else None)
+            if track and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+            world = 1
+        else:
+            mi, ss, world = _finalize_stats(ops.bn_merge_partials(sp, tc), bn, pg)
         y = ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)
         ctx.save_for_backward(x, raw, y if relu else None, mi, gamma)
         ctx.pw, ctx.k, ctx.dil, ctx.relu, ctx.pg, ctx.world = pw, k, dil, relu, pg, world
@@ -216,6 +224,77 @@ def conv_bias_f32(x, conv):
     pw = packed(conv, need_dgrad=False)
     y, _, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(1, 1), epi=EPI_F32, shift=conv.bias)
     return y
+
+
+# ------------------------------------------------------------------------------------------------ fused tail
+class _UpsampleCE(torch.autograd.Function):
+    """bilinear x8 upsample (align_corners) + CrossEntropyLoss(ignore_index, mean) + argmax in one kernel each way
+    (model/pspnet.py:94-103) — the [N, classes, H, W] logits tensor is never materialised."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        info, amax, lse = ops.upsample_ce_fwd(logits, target, ignore_index)
+        ctx.save_for_backward(logits, target, lse, info)
+        ctx.ignore_index = ignore_index
+        ctx.mark_non_differentiable(amax)
+        return info[0], amax
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_amax):
+        logits, target, lse, info = ctx.saved_tensors
+        return ops.upsample_ce_bwd(logits, target, ctx.ignore_index, lse, info, grad_loss), None, None
+
+
+def fused_tail_supported(criterion, logits, target, zoom_factor):
+    """The fused kernel implements exactly nn.CrossEntropyLoss(ignore_index=k) with default options at zoom 8."""
+    return (type(criterion) is nn.CrossEntropyLoss and criterion.weight is None and criterion.reduction == 'mean'
+            and getattr(criterion, 'label_smoothing', 0.0) == 0.0 and zoom_factor == 8 and target is not None
+            and target.dtype == torch.int64 and target.dim() == 3 and logits.shape[-1] <= 256
+            and target.shape[1] == 8 * (logits.shape[1] - 1) + 1 and target.shape[2] == 8 * (logits.shape[2] - 1) + 1)
+
+
+def upsample_ce(logits, target, ignore_index):
+    """-> (mean CE loss scalar, argmax int64 [N,H,W])."""
+    return _UpsampleCE.apply(logits, target.contiguous(), ignore_index)
+
+
+# ------------------------------------------------------------------------------------------------ pyramid pooling
+class _PPMPool(torch.autograd.Function):
+    """AdaptiveAvgPool2d of every bin in one launch (model/pspnet.py:14)."""
+
+    @staticmethod
+    def forward(ctx, x, bins):
+        ctx.bins, ctx.shape = bins, tuple(x.shape)
+        return tuple(ops.ppm_pool(x, bins))
+
+    @staticmethod
+    def backward(ctx, *dpooled):
+        n, h, w, c = ctx.shape
+        return ops.ppm_pool_bwd(list(dpooled), ctx.bins, n, h, w, c), None
+
+
+class _PPMUpsampleConcat(torch.autograd.Function):
+    """cat([x, bilinear(f_1), ..., bilinear(f_nb)], channel) written in place (model/pspnet.py:25-26)."""
+
+    @staticmethod
+    def forward(ctx, x, bins, *feats):
+        ctx.bins, ctx.c, ctx.cr = bins, x.shape[-1], feats[0].shape[-1]
+        return ops.ppm_upsample_concat(x, list(feats), bins)
+
+    @staticmethod
+    def backward(ctx, dout):
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        dfeats = ops.ppm_upsample_bwd(dout, ctx.c, ctx.bins, ctx.cr)
+        return (dout[..., :ctx.c], None) + tuple(dfeats)
+
+
+def ppm_pool(x, bins):
+    return _PPMPool.apply(x, tuple(bins))
+
+
+def ppm_upsample_concat(x, feats, bins):
+    return _PPMUpsampleConcat.apply(x, tuple(bins), *feats)
 
 
 # ------------------------------------------------------------------------------------------------ misc NHWC ops

@@ -275,6 +275,18 @@ def bn_finalize(rank_stats, gamma, beta, eps, momentum, running_mean, running_va
     return mi, ss
 
 
+def bn_finalize_partials(stats_partial, tile_count, gamma, beta, eps, momentum, running_mean, running_var):
+    """Per-tile conv partials -> (mean_invstd, scale_shift) in one launch (single-rank BatchNorm)."""
+    lib = _lib.load()
+    t, _, c = stats_partial.shape
+    buf = torch.empty((4, c), dtype=torch.float32, device=stats_partial.device)
+    mi, ss = buf[:2], buf[2:]
+    _lib.check(lib.semseg_bn_finalize_partials(_ptr(stats_partial), _ptr(tile_count), t, c, _ptr(gamma), _ptr(beta),
+                                               float(eps), float(momentum), _ptr(running_mean), _ptr(running_var),
+                                               _ptr(mi), _ptr(ss), _stream()), "semseg_bn_finalize_partials")
+    return mi, ss
+
+
 def bn_fold_eval(gamma, beta, running_mean, running_var, eps):
     lib = _lib.load()
     c = running_mean.numel()
@@ -350,3 +362,86 @@ def add_bf16(a, b, out=None):
     _lib.check(lib.semseg_add_bf16(_ptr(a), ap, _ptr(b), bp, _ptr(out), op, n * h * w, c, _stream()),
                "semseg_add_bf16")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ fused tail
+def upsample_ce_fwd(logits, target, ignore_index, want_argmax=True):
+    """logits fp32 NHWC [N,h,w,C], target int64 [N,Ho,Wo] -> (loss_info [2] = (mean CE, count), argmax, lse)."""
+    _require_cuda(logits, target)
+    lib = _lib.load()
+    assert logits.dtype == torch.float32 and logits.dim() == 4 and logits.stride(-1) == 1
+    assert target.dtype == torch.int64 and target.is_contiguous()
+    n, h, w, c = logits.shape
+    _, ho, wo = target.shape
+    nws = int(lib.semseg_upsample_ce_workspace_floats(n, ho, wo))
+    ws = torch.empty((nws,), dtype=torch.float32, device=logits.device)
+    info = torch.empty((2,), dtype=torch.float32, device=logits.device)
+    amax = torch.empty((n, ho, wo), dtype=torch.int64, device=logits.device) if want_argmax else None
+    lse = torch.empty((n, ho, wo), dtype=torch.float32, device=logits.device)
+    _lib.check(lib.semseg_upsample_ce_fwd(_ptr(logits), logits.stride(2), n, h, w, c, _ptr(target), ho, wo,
+                                          int(ignore_index), _ptr(ws), _ptr(info), _ptr(amax), _ptr(lse), _stream()),
+               "semseg_upsample_ce_fwd")
+    return info, amax, lse
+
+
+def upsample_ce_bwd(logits, target, ignore_index, lse, info, grad_out):
+    lib = _lib.load()
+    n, h, w, c = logits.shape
+    _, ho, wo = target.shape
+    dl = torch.empty((n, h, w, c), dtype=torch.float32, device=logits.device)
+    g = grad_out.reshape(1).float().contiguous()
+    _lib.check(lib.semseg_upsample_ce_bwd(_ptr(logits), logits.stride(2), n, h, w, c, _ptr(target), ho, wo,
+                                          int(ignore_index), _ptr(lse), _ptr(info), _ptr(g), _ptr(dl), _stream()),
+               "semseg_upsample_ce_bwd")
+    return dl
+
+
+# ------------------------------------------------------------------------------------------------ pyramid pooling
+def _bin_args(bins, tensors):
+    nb = len(bins)
+    barr = (ctypes.c_int * nb)(*bins)
+    parr = (ctypes.c_void_p * nb)(*[t.data_ptr() for t in tensors])
+    return barr, parr, nb
+
+
+def ppm_pool(x, bins):
+    """x NHWC bf16 -> [pooled_k [N,b,b,C] bf16 for b in bins] (AdaptiveAvgPool2d of every bin, one launch)."""
+    _require_cuda(x)
+    lib = _lib.load()
+    n, h, w, c, p = _nhwc_meta(x)
+    outs = [torch.empty((n, b, b, c), dtype=torch.bfloat16, device=x.device) for b in bins]
+    barr, parr, nb = _bin_args(bins, outs)
+    _lib.check(lib.semseg_ppm_pool(_ptr(x), p, n, h, w, c, barr, parr, nb, _stream()), "semseg_ppm_pool")
+    return outs
+
+
+def ppm_pool_bwd(dpooled, bins, n, h, w, c):
+    lib = _lib.load()
+    dpooled = [d.contiguous() for d in dpooled]
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dpooled[0].device)
+    barr, parr, nb = _bin_args(bins, dpooled)
+    _lib.check(lib.semseg_ppm_pool_bwd(parr, barr, nb, n, h, w, c, _ptr(dx), c, _stream()), "semseg_ppm_pool_bwd")
+    return dx
+
+
+def ppm_upsample_concat(x, feats, bins):
+    """-> out [N,H,W,C + nb*Cr] bf16 = cat([x, bilinear(feats_k)...], channel)."""
+    lib = _lib.load()
+    n, h, w, c, p = _nhwc_meta(x)
+    feats = [f.contiguous() for f in feats]
+    cr = feats[0].shape[-1]
+    out = torch.empty((n, h, w, c + len(bins) * cr), dtype=torch.bfloat16, device=x.device)
+    barr, parr, nb = _bin_args(bins, feats)
+    _lib.check(lib.semseg_ppm_upsample_concat(_ptr(x), p, parr, barr, nb, n, h, w, c, cr, _ptr(out),
+                                              out.shape[-1], _stream()), "semseg_ppm_upsample_concat")
+    return out
+
+
+def ppm_upsample_bwd(dout, c_off, bins, cr):
+    lib = _lib.load()
+    n, h, w, ct, p = _nhwc_meta(dout)
+    dfeats = [torch.empty((n, b, b, cr), dtype=torch.bfloat16, device=dout.device) for b in bins]
+    barr, parr, nb = _bin_args(bins, dfeats)
+    _lib.check(lib.semseg_ppm_upsample_bwd(_ptr(dout), p, c_off, parr, barr, nb, n, h, w, cr, _stream()),
+               "semseg_ppm_upsample_bwd")
+    return dfeats

@@ -180,8 +180,14 @@ class PSANet(nn.Module):
         logits = head_forward_nhwc(self.cls, t)
 
         if self.training:
+            aux_logits = head_forward_nhwc(self.aux, t_tmp)
+            if SF.fused_tail_supported(self.criterion, logits, y, self.zoom_factor):
+                # upsample + cross-entropy + argmax fused: [N, classes, H, W] never exists (model/pspnet.py:94-103)
+                main_loss, pred = SF.upsample_ce(logits, y, self.criterion.ignore_index)
+                aux_loss, _ = SF.upsample_ce(aux_logits, y, self.criterion.ignore_index)
+                return pred, main_loss, aux_loss
             x = upsample_logits(logits, (h, w), self.zoom_factor)
-            aux = upsample_logits(head_forward_nhwc(self.aux, t_tmp), (h, w), self.zoom_factor)
+            aux = upsample_logits(aux_logits, (h, w), self.zoom_factor)
             main_loss = self.criterion(x, y)
             aux_loss = self.criterion(aux, y)
             return x.max(1)[1], main_loss, aux_loss

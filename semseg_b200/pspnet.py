@@ -28,15 +28,13 @@ class PPM(nn.Module):
         self.features = nn.ModuleList(self.features)
 
     def forward_nhwc(self, x):
-        n, h, w, c = x.shape
-        xn = x.permute(0, 3, 1, 2)
-        out = [x]
+        bins = []
         for f in self.features:
-            p = F.adaptive_avg_pool2d(xn, f[0].output_size).permute(0, 2, 3, 1).contiguous()
-            y = SF.conv_bn_act(p, f[1], f[2], relu=True)
-            up = F.interpolate(y.permute(0, 3, 1, 2), (h, w), mode='bilinear', align_corners=True)
-            out.append(up.permute(0, 2, 3, 1))
-        return torch.cat(out, 3)
+            b = f[0].output_size
+            bins.append(b if isinstance(b, int) else b[0])
+        pooled = SF.ppm_pool(x, bins)                      # one launch: every bin's AdaptiveAvgPool2d
+        feats = [SF.conv_bn_act(p, f[1], f[2], relu=True) for p, f in zip(pooled, self.features)]
+        return SF.ppm_upsample_concat(x, feats, bins)      # one launch: upsample x4 + concat, written in place
 
     def forward(self, x):
         y = self.forward_nhwc(SF.to_nhwc_bf16(x))
@@ -128,8 +126,14 @@ class PSPNet(nn.Module):
         logits = head_forward_nhwc(self.cls, t)
 
         if self.training:
+            aux_logits = head_forward_nhwc(self.aux, t_tmp)
+            if SF.fused_tail_supported(self.criterion, logits, y, self.zoom_factor):
+                # upsample + cross-entropy + argmax fused: [N, classes, H, W] never exists (model/pspnet.py:94-103)
+                main_loss, pred = SF.upsample_ce(logits, y, self.criterion.ignore_index)
+                aux_loss, _ = SF.upsample_ce(aux_logits, y, self.criterion.ignore_index)
+                return pred, main_loss, aux_loss
             x = upsample_logits(logits, (h, w), self.zoom_factor)
-            aux = upsample_logits(head_forward_nhwc(self.aux, t_tmp), (h, w), self.zoom_factor)
+            aux = upsample_logits(aux_logits, (h, w), self.zoom_factor)
             main_loss = self.criterion(x, y)
             aux_loss = self.criterion(aux, y)
             return x.max(1)[1], main_loss, aux_loss
