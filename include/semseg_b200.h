@@ -95,14 +95,13 @@ typedef struct semseg_conv_desc {
   int32_t res_pitch;
   float* out_f32; /* F32 mode output */
   int32_t out_pitch;
-  /* RAW mode statistics: stats_partial [num_m_tiles][2][Cout] (sum, M2 about the tile mean),
-   * tile_count [num_m_tiles]; NULL to skip. num_m_tiles from semseg_conv_num_m_tiles(). */
+  /* RAW mode statistics: stats_partial [rows][3][Cout] = per-CTA (sum, sum of squares, count) of the stored bf16
+   * outputs per channel, rows = semseg_conv_stats_rows(); NULL to skip. The kernel zeroes and fills every row. */
   float* stats_partial;
-  float* tile_count;
 } semseg_conv_desc;
 
-/* Number of pixel tiles the kernel will use for an [N,H,W] output grid (size of the stats buffers). */
-int semseg_conv_num_m_tiles(int N, int H, int W);
+/* Rows of the statistics buffer (= CTAs launched) for an [N,H,W] x Cout output. */
+int semseg_conv_stats_rows(int N, int H, int W, int Cout);
 int semseg_conv_fprop(const semseg_conv_desc* d, void* stream);
 
 /* wgrad: dw_partial[split][tap][co][ci] (fp32) = sum over the split's pixels of dy[p, co] * x[p + off(tap), ci].
@@ -148,9 +147,8 @@ int semseg_nhwc_f32_to_nchw_f32(const float* in, float* out, int N, int C, int H
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm (training statistics, apply, backward) on NHWC bf16 tensors, fp32 statistics.
  */
-/* Merge per-tile partials (Chan) into per-channel (mean, M2, count): out_stats [3][C]. */
-int semseg_bn_merge_partials(const float* stats_partial, const float* tile_count, int num_tiles, int C,
-                             float* out_stats, void* stream);
+/* Merge the conv epilogue's per-CTA partials [rows][3][C] (Chan) into per-channel (mean, M2, count): out_stats [3][C]. */
+int semseg_bn_merge_partials(const float* stats_partial, int rows, int C, float* out_stats, void* stream);
 /* Per-channel statistics of an arbitrary NHWC bf16 tensor [M pixels][C] (used where the producer is not the
  * conv kernel): out_stats [3][C] = (mean, M2, count). */
 int semseg_bn_stats(const void* x, int M, int C, int pitch, float* workspace, long long workspace_floats,
@@ -164,8 +162,7 @@ int semseg_bn_finalize(const float* rank_stats, int R, int C, const float* gamma
                        float momentum, float* running_mean, float* running_var, float* mean_invstd,
                        float* scale_shift, void* stream);
 /* Single-rank fast path: semseg_bn_merge_partials + semseg_bn_finalize (R = 1) in one launch. */
-int semseg_bn_finalize_partials(const float* stats_partial, const float* tile_count, int num_tiles, int C,
-                                const float* gamma, const float* beta, float eps, float momentum,
+int semseg_bn_finalize_partials(const float* stats_partial, int rows, int C, const float* gamma, const float* beta, float eps, float momentum,
                                 float* running_mean, float* running_var, float* mean_invstd, float* scale_shift,
                                 void* stream);
 /* Eval-mode folding: scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */

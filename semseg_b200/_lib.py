@@ -37,7 +37,7 @@ class ConvDesc(ctypes.Structure):
         ("scale", c_vp), ("shift", c_vp),
         ("residual", c_vp), ("res_pitch", c_i32),
         ("out_f32", c_vp), ("out_pitch", c_i32),
-        ("stats_partial", c_vp), ("tile_count", c_vp),
+        ("stats_partial", c_vp),
     ]
 
 
@@ -65,7 +65,7 @@ SIGNATURES = {
     "semseg_launch_count": (c_ll, []),
     "semseg_psamask_fwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_psamask_bwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
-    "semseg_conv_num_m_tiles": (c_int, [c_int, c_int, c_int]),
+    "semseg_conv_stats_rows": (c_int, [c_int, c_int, c_int, c_int]),
     "semseg_conv_fprop": (c_int, [ctypes.POINTER(ConvDesc), c_vp]),
     "semseg_conv_wgrad_splits": (c_int, [ctypes.POINTER(WgradDesc)]),
     "semseg_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_vp]),
@@ -74,12 +74,11 @@ SIGNATURES = {
     "semseg_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_nhwc_f32_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
-    "semseg_bn_merge_partials": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "semseg_bn_merge_partials": (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
     "semseg_bn_stats": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_ll, c_vp, c_vp]),
     "semseg_bn_workspace_floats": (c_ll, [c_int, c_int]),
     "semseg_bn_finalize": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "semseg_bn_finalize_partials": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp,
-                                            c_vp]),
+    "semseg_bn_finalize_partials": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "semseg_bn_fold_eval": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_vp, c_vp]),
     "semseg_bn_apply": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_bn_bwd_reduce": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp, c_ll,

@@ -55,10 +55,43 @@ __global__ void bn_merge_partials_kernel(const float* __restrict__ part, const f
   }
 }
 
+// Row of the conv epilogue's statistics buffer [rows][3][C] = (sum, sum of squares, count) -> Moments.
+__device__ __forceinline__ Moments conv_row_moments(const float* __restrict__ part, int t, int C, int c) {
+  Moments m = {0.f, 0.f, 0.f};
+  const float* row = part + static_cast<size_t>(t) * 3 * C;
+  const float n = row[2 * C + c];
+  if (n > 0.f) {
+    const float s = row[c], q = row[C + c];
+    m.n = n;
+    m.mean = s / n;
+    m.m2 = fmaxf(q - s * m.mean, 0.f);
+  }
+  return m;
+}
+
+__global__ void bn_merge_conv_partials_kernel(const float* __restrict__ part, int T, int C, float* __restrict__ out) {
+  __shared__ Moments sm[32][33];
+  const int cl = threadIdx.x & 31;
+  const int tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  Moments acc = {0.f, 0.f, 0.f};
+  if (c < C)
+    for (int t = tl; t < T; t += 32) acc = merge(acc, conv_row_moments(part, t, C, c));
+  sm[tl][cl] = acc;
+  __syncthreads();
+  if (tl == 0 && c < C) {
+    Moments r = sm[0][cl];
+    for (int i = 1; i < 32; ++i) r = merge(r, sm[i][cl]);
+    out[c] = r.mean;
+    out[C + c] = r.m2;
+    out[2 * C + c] = r.n;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Single-rank fast path: merge the per-tile partials AND finalise in one launch (no SyncBN exchange needed).
-__global__ void bn_finalize_partials_kernel(const float* __restrict__ part, const float* __restrict__ cnt, int T,
-                                            int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+__global__ void bn_finalize_partials_kernel(const float* __restrict__ part, int T, int C,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                             float eps, float momentum, float* __restrict__ running_mean,
                                             float* __restrict__ running_var, float* __restrict__ mean_invstd,
                                             float* __restrict__ scale_shift) {
@@ -67,18 +100,8 @@ __global__ void bn_finalize_partials_kernel(const float* __restrict__ part, cons
   const int tl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   Moments acc = {0.f, 0.f, 0.f};
-  if (c < C) {
-    for (int t = tl; t < T; t += 32) {
-      const float n = cnt[t];
-      if (n > 0.f) {
-        Moments m;
-        m.n = n;
-        m.mean = part[(static_cast<size_t>(t) * 2) * C + c] / n;
-        m.m2 = part[(static_cast<size_t>(t) * 2 + 1) * C + c];
-        acc = merge(acc, m);
-      }
-    }
-  }
+  if (c < C)
+    for (int t = tl; t < T; t += 32) acc = merge(acc, conv_row_moments(part, t, C, c));
   sm[tl][cl] = acc;
   __syncthreads();
   if (tl == 0 && c < C) {
@@ -465,23 +488,22 @@ extern "C" long long semseg_bn_workspace_floats(int M, int C) {
   return chunks * 2 * C + chunks + 3LL * C;
 }
 
-extern "C" int semseg_bn_merge_partials(const float* stats_partial, const float* tile_count, int num_tiles, int C,
-                                        float* out_stats, void* stream_) {
+extern "C" int semseg_bn_merge_partials(const float* stats_partial, int rows, int C, float* out_stats, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SB_CHECK_ARG(stats_partial && tile_count && out_stats && num_tiles > 0 && C > 0, "bn_merge_partials: bad args");
-  bn_merge_partials_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, tile_count, num_tiles, C, out_stats);
+  SB_CHECK_ARG(stats_partial && out_stats && rows > 0 && C > 0, "bn_merge_partials: bad args");
+  bn_merge_conv_partials_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, rows, C, out_stats);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
 
-extern "C" int semseg_bn_finalize_partials(const float* stats_partial, const float* tile_count, int num_tiles, int C,
+extern "C" int semseg_bn_finalize_partials(const float* stats_partial, int num_tiles, int C,
                                            const float* gamma, const float* beta, float eps, float momentum,
                                            float* running_mean, float* running_var, float* mean_invstd,
                                            float* scale_shift, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SB_CHECK_ARG(stats_partial && tile_count && mean_invstd && scale_shift && num_tiles > 0 && C > 0,
+  SB_CHECK_ARG(stats_partial && mean_invstd && scale_shift && num_tiles > 0 && C > 0,
                "bn_finalize_partials: bad args");
-  bn_finalize_partials_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, tile_count, num_tiles, C, gamma, beta,
+  bn_finalize_partials_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, num_tiles, C, gamma, beta,
                                                                eps, momentum, running_mean, running_var, mean_invstd,
                                                                scale_shift);
   SB_LAUNCHED();

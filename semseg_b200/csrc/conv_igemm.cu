@@ -53,8 +53,7 @@ struct ConvKParams {
   int res_pitch;
   float* out_f32;
   int out_pitch;
-  float* stats_partial;
-  float* tile_count;
+  float* stats_partial;  // [gridDim.x][3][Cout]: per-CTA (sum, sum of squares, count) per output channel
 };
 
 template <int BLOCK_N>
@@ -100,6 +99,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 1) {
     tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  }
+  if (p.stats_partial != nullptr) {
+    float* row = p.stats_partial + static_cast<size_t>(blockIdx.x) * 3 * p.Cout;
+    for (int i = threadIdx.x; i < 3 * p.Cout; i += kNumThreads) row[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -323,14 +326,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             const float nt = static_cast<float>(__popc(row_mask[0]) + __popc(row_mask[1]) + __popc(row_mask[2]) +
                                                 __popc(row_mask[3]));
-            const float inv = nt > 0.f ? 1.f / nt : 0.f;
-            float* dst = p.stats_partial + static_cast<size_t>(m_tile) * 2 * p.Cout;
+            // Per-CTA running (sum, sum of squares, count) per column: this CTA is the only writer of its row and
+            // a given column is always handled by the same thread, so plain read-modify-write is race free and
+            // the accumulation order (this CTA's tile sequence) is fixed -> deterministic.
+            float* dst = p.stats_partial + static_cast<size_t>(blockIdx.x) * 3 * p.Cout;
             const int col = c0 + 2 * cp;
-            dst[col] = S0;
-            dst[col + 1] = S1;
-            dst[p.Cout + col] = fmaxf(Q0 - S0 * S0 * inv, 0.f);
-            dst[p.Cout + col + 1] = fmaxf(Q1 - S1 * S1 * inv, 0.f);
-            if (n_tile == 0 && ch == 0 && cp == 0 && p.tile_count) p.tile_count[m_tile] = nt;
+            dst[col] += S0;
+            dst[col + 1] += S1;
+            dst[p.Cout + col] += Q0;
+            dst[p.Cout + col + 1] += Q1;
+            dst[2 * p.Cout + col] += nt;
+            dst[2 * p.Cout + col + 1] += nt;
           }
           named_bar_sync(2, kEpiThreads);  // scratch may be rewritten by the next chunk
         }
@@ -370,10 +376,20 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 }  // namespace sb
 
-extern "C" int semseg_conv_num_m_tiles(int N, int H, int W) {
+static int conv_block_n(int Cout) {
+  if (Cout % 256 == 0 || Cout > 128) return 256;
+  return Cout > 64 ? 128 : 64;
+}
+
+// Rows of the RAW-epilogue statistics buffer = number of CTAs the kernel will launch for this problem.
+extern "C" int semseg_conv_stats_rows(int N, int H, int W, int Cout) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cout <= 0) return SEMSEG_E_INVALID;
   int bh, bw;
   sb::choose_box(H, W, sb::kBlockM, &bh, &bw);
-  return N * sb::cdiv(H, bh) * sb::cdiv(W, bw);
+  const long long tiles =
+      static_cast<long long>(N) * sb::cdiv(H, bh) * sb::cdiv(W, bw) * sb::cdiv(Cout, conv_block_n(Cout));
+  const int sms = sb::num_sms();
+  return static_cast<int>(tiles < sms ? tiles : sms);
 }
 
 extern "C" int semseg_conv_fprop(const semseg_conv_desc* d, void* stream_) {
@@ -406,12 +422,9 @@ extern "C" int semseg_conv_fprop(const semseg_conv_desc* d, void* stream_) {
   kp.scale = d->scale; kp.shift = d->shift;
   kp.residual = static_cast<const __nv_bfloat16*>(d->residual); kp.res_pitch = d->res_pitch;
   kp.out_f32 = d->out_f32; kp.out_pitch = d->out_pitch;
-  kp.stats_partial = d->stats_partial; kp.tile_count = d->tile_count;
+  kp.stats_partial = d->stats_partial;
 
-  int block_n;
-  if (d->Cout % 256 == 0 || d->Cout > 128) block_n = 256;
-  else if (d->Cout > 64) block_n = 128;
-  else block_n = 64;
+  const int block_n = conv_block_n(d->Cout);
   kp.n_tiles = cdiv(d->Cout, block_n);
 
   // A: input activations [Nin][Hin][Win][x_pitch] viewed as (C, W, H, N)

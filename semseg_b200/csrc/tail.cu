@@ -202,41 +202,49 @@ upsample_ce_bwd_kernel(const float* __restrict__ logits, int pitch, int N, int h
       // lane group = interval (x>>3); the group's left node is xj0, right node xj0+1.
       // group index within this warp: lane>>3 (0..3); global interval column jv = (j0-1) + half*4 + (lane>>3).
       const int grp = lane >> 3;
-      for (int c = 0; c < C; ++c) {
-        float g = 0.f;
-        if (contributes) {
-          const float v =
-              l0h * (l0w * r0[cj0 + c] + l1w * r0[cj1 + c]) + l1h * (l0w * r1[cj0 + c] + l1w * r1[cj1 + c]);
-          g = (__expf(v - lsev) - (c == t ? 1.f : 0.f)) * gscale;
+      // KC classes per iteration: all shared-memory reads first, then the shuffle butterflies interleaved, then
+      // the stores (T/A alias S for the compiler, so without this the loop serialises on ~7 dependent shuffles).
+      constexpr int KC = 5;
+      float* stash = A + kOwnI * kOwnJ * C + r * C;
+      for (int cb = 0; cb < C; cb += KC) {
+        float a[KC], b[KC];
+#pragma unroll
+        for (int u = 0; u < KC; ++u) {
+          const int c = cb + u;
+          float g = 0.f;
+          if (contributes && c < C) {
+            const float v =
+                l0h * (l0w * r0[cj0 + c] + l1w * r0[cj1 + c]) + l1h * (l0w * r1[cj0 + c] + l1w * r1[cj1 + c]);
+            g = (__expf(v - lsev) - (c == t ? 1.f : 0.f)) * gscale;
+          }
+          a[u] = l0w * g;  // contribution to the left node of this pixel's interval
+          b[u] = l1w * g;  // ... and to the right node
         }
-        float a = l0w * g, b = l1w * g;  // contribution to the left / right node of this interval
         // reduce inside the 8-lane interval group (fixed butterfly order -> deterministic)
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        b += __shfl_xor_sync(0xffffffffu, b, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        b += __shfl_xor_sync(0xffffffffu, b, 2);
-        a += __shfl_xor_sync(0xffffffffu, a, 4);
-        b += __shfl_xor_sync(0xffffffffu, b, 4);
-        // node (j0 - 1 + half*4 + grp) receives a, node (+1) receives b. Owned nodes are jo = 0..6 <-> node j0+jo.
-        // left-node index relative to owned: jl = half*4 + grp - 1 ; right-node: jl + 1.
-        // Combine so that each owned node is written by exactly one lane: node jo gets a(group jo+1-half*4) +
-        // b(group jo-half*4). Fetch the previous group's b via shuffle.
-        const float b_prev = __shfl_up_sync(0xffffffffu, b, 8);  // b of group grp-1 (same warp)
-        if ((lane & 7) == 0) {
-          const int jl = half * 4 + grp - 1;  // owned index of this group's left node
-          if (half == 0) {
-            // groups 0..3 -> left nodes -1,0,1,2. node jl (>=0) = a(this) + b(prev group)
-            if (grp >= 1) T[(r * kOwnJ + jl) * C + c] = a + b_prev;
-          } else {
-            // groups 0..3 -> left nodes 3,4,5,6; b_prev for grp 0 comes from the other warp (half 0, group 3)
-            if (grp >= 1) T[(r * kOwnJ + jl) * C + c] = a + b_prev;
-            else T[(r * kOwnJ + jl) * C + c] = a;  // + b of (half 0, grp 3), added below
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+          for (int u = 0; u < KC; ++u) {
+            a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
+            b[u] += __shfl_xor_sync(0xffffffffu, b[u], o);
           }
         }
-        // cross-warp term: owned node 3 also needs b of (half 0, group 3), which lives in the other warp.
-        if (half == 0 && lane == 24) {
-          // stash b of group 3 for node jo = 3 in a dedicated slot after the accumulators
-          A[kOwnI * kOwnJ * C + r * C + c] = b;
+        float bp[KC];
+#pragma unroll
+        for (int u = 0; u < KC; ++u) bp[u] = __shfl_up_sync(0xffffffffu, b[u], 8);  // b of the previous group
+        // Interval group (half, grp) has left node jl = half*4 + grp - 1 (owned index). Owned node jo receives
+        // a(group with jl == jo) + b(group with jl == jo - 1); exactly one lane writes each T entry.
+        if ((lane & 7) == 0) {
+          const int jl = half * 4 + grp - 1;
+#pragma unroll
+          for (int u = 0; u < KC; ++u) {
+            const int c = cb + u;
+            if (c < C) {
+              if (grp >= 1) T[(r * kOwnJ + jl) * C + c] = a[u] + bp[u];
+              else if (half == 1) T[(r * kOwnJ + jl) * C + c] = a[u];  // + b of (half 0, grp 3): stashed below
+              if (half == 0 && grp == 3) stash[c] = b[u];              // cross-warp term for owned node 3
+            }
+          }
         }
       }
     }

@@ -87,18 +87,18 @@ class _ConvBnAct(torch.autograd.Function):
     def forward(ctx, x, weight, gamma, beta, residual, conv, bn, relu, out):
         pw = packed(conv)
         k, dil = conv.kernel_size[0], conv.dilation[0]
-        raw, sp, tc = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(k, dil), stats=True)
+        raw, sp = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(k, dil), stats=True)
         pg = _sync_group(bn)
         if pg is None:
             # single rank: merge the per-tile partials and finalise in one launch
             track = bn.track_running_stats and bn.running_mean is not None
-            mi, ss = ops.bn_finalize_partials(sp, tc, bn.weight, bn.bias, bn.eps, _bn_momentum(bn) if track else 0.0,
+            mi, ss = ops.bn_finalize_partials(sp, bn.weight, bn.bias, bn.eps, _bn_momentum(bn) if track else 0.0,
                                               bn.running_mean if track else None, bn.running_var if track else None)
             if track and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked.add_(1)
             world = 1
         else:
-            mi, ss, world = _finalize_stats(ops.bn_merge_partials(sp, tc), bn, pg)
+            mi, ss, world = _finalize_stats(ops.bn_merge_partials(sp), bn, pg)
         y = ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)
         ctx.save_for_backward(x, raw, y if relu else None, mi, gamma)
         ctx.pw, ctx.k, ctx.dil, ctx.relu, ctx.pg, ctx.world = pw, k, dil, relu, pg, world
@@ -115,7 +115,7 @@ class _ConvBnAct(torch.autograd.Function):
                                                   ctx.has_res and ctx.needs_input_grad[4])
         dx = None
         if ctx.needs_input_grad[0]:
-            dx, _, _ = ops.conv_fprop(d_raw, pw.wd, pw.cin, ops.conv_taps(ctx.k, ctx.dil, transpose=True))
+            dx, _ = ops.conv_fprop(d_raw, pw.wd, pw.cin, ops.conv_taps(ctx.k, ctx.dil, transpose=True))
         dw = None
         if ctx.needs_input_grad[1]:
             dw = ops.conv_wgrad(x, d_raw, pw.cin, pw.cout, ops.conv_taps(ctx.k, ctx.dil))
@@ -171,7 +171,7 @@ def conv_bn_act(x, conv, bn, relu=True, residual=None, out=None):
                                       "run eval under torch.no_grad()")
         if native:
             pw = packed(conv, need_dgrad=False)
-            y, _, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(conv.kernel_size[0], conv.dilation[0]),
+            y, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(conv.kernel_size[0], conv.dilation[0]),
                                      epi=EPI_AFFINE, relu=relu, scale=ss[0], shift=ss[1], residual=residual, out=out)
             return y
         raw = _library_conv(x, conv)
@@ -193,7 +193,7 @@ class _ConvBiasF32(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, conv):
         pw = packed(conv)
-        y, _, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(1, 1), epi=EPI_F32, shift=bias)
+        y, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(1, 1), epi=EPI_F32, shift=bias)
         ctx.save_for_backward(x)
         ctx.pw = pw
         return y
@@ -208,7 +208,7 @@ class _ConvBiasF32(torch.autograd.Function):
         dyb[..., :c] = dy
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx, _, _ = ops.conv_fprop(dyb, pw.wd, pw.cin, ops.conv_taps(1, 1))
+            dx, _ = ops.conv_fprop(dyb, pw.wd, pw.cin, ops.conv_taps(1, 1))
         if ctx.needs_input_grad[1]:
             dwp = ops.conv_wgrad(x, dyb, pw.cin, cp, ops.conv_taps(1, 1))
             dw = dwp[:c].contiguous()
@@ -222,7 +222,7 @@ def conv_bias_f32(x, conv):
     if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
         return _ConvBiasF32.apply(x, conv.weight, conv.bias, conv)
     pw = packed(conv, need_dgrad=False)
-    y, _, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(1, 1), epi=EPI_F32, shift=conv.bias)
+    y, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(1, 1), epi=EPI_F32, shift=conv.bias)
     return y
 
 

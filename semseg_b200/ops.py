@@ -114,15 +114,16 @@ def _fill_taps(desc, taps, with_wtap=True):
 
 
 # ------------------------------------------------------------------------------------------------ conv
-def conv_num_m_tiles(n, h, w):
-    return int(_lib.load().semseg_conv_num_m_tiles(n, h, w))
+def conv_stats_rows(n, h, w, cout):
+    return int(_lib.load().semseg_conv_stats_rows(n, h, w, cout))
 
 
 def conv_fprop(x, w3d, cout, taps, *, out=None, epi=EPI_RAW, relu=False, scale=None, shift=None, residual=None,
                stats=False, out_f32=None):
     """Implicit-GEMM conv of NHWC bf16 `x` with packed weights `w3d` [n_wtaps][rows][cols].
 
-    Returns (y, stats_partial, tile_count); y is bf16 NHWC [N,H,W,cout] (or the fp32 tensor in F32 mode).
+    Returns (y, stats_partial); y is bf16 NHWC [N,H,W,cout] (or the fp32 tensor in F32 mode); stats_partial is the
+    per-CTA [rows][3][cout] (sum, sum of squares, count) buffer when stats=True.
     """
     _require_cuda(x, w3d)
     lib = _lib.load()
@@ -134,7 +135,7 @@ def conv_fprop(x, w3d, cout, taps, *, out=None, epi=EPI_RAW, relu=False, scale=N
     d.w, d.n_wtaps, d.w_rows, d.w_cols = w3d.data_ptr(), w3d.shape[0], w3d.shape[1], w3d.shape[2]
     _fill_taps(d, taps)
     d.epi_mode, d.relu = epi, int(bool(relu))
-    sp = tc = None
+    sp = None
     if epi == EPI_F32:
         if out_f32 is None:
             out_f32 = torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
@@ -160,12 +161,10 @@ def conv_fprop(x, w3d, cout, taps, *, out=None, epi=EPI_RAW, relu=False, scale=N
         d.residual, d.res_pitch = residual.data_ptr(), rp
     if stats:
         assert epi == EPI_RAW
-        mt = conv_num_m_tiles(n, h, w)
-        sp = torch.empty((mt, 2, cout), dtype=torch.float32, device=x.device)
-        tc = torch.empty((mt,), dtype=torch.float32, device=x.device)
-        d.stats_partial, d.tile_count = sp.data_ptr(), tc.data_ptr()
+        sp = torch.empty((conv_stats_rows(n, h, w, cout), 3, cout), dtype=torch.float32, device=x.device)
+        d.stats_partial = sp.data_ptr()
     _lib.check(lib.semseg_conv_fprop(ctypes.byref(d), _stream()), "semseg_conv_fprop")
-    return y, sp, tc
+    return y, sp
 
 
 def conv_wgrad(x, dy, cin, cout, taps, grad_out=None, accumulate=False):
@@ -239,11 +238,11 @@ def bn_workspace(m, c, device):
     return torch.empty((nf,), dtype=torch.float32, device=device), nf
 
 
-def bn_merge_partials(stats_partial, tile_count):
+def bn_merge_partials(stats_partial):
     lib = _lib.load()
     t, _, c = stats_partial.shape
     out = torch.empty((3, c), dtype=torch.float32, device=stats_partial.device)
-    _lib.check(lib.semseg_bn_merge_partials(_ptr(stats_partial), _ptr(tile_count), t, c, _ptr(out), _stream()),
+    _lib.check(lib.semseg_bn_merge_partials(_ptr(stats_partial), t, c, _ptr(out), _stream()),
                "semseg_bn_merge_partials")
     return out
 
@@ -275,13 +274,13 @@ def bn_finalize(rank_stats, gamma, beta, eps, momentum, running_mean, running_va
     return mi, ss
 
 
-def bn_finalize_partials(stats_partial, tile_count, gamma, beta, eps, momentum, running_mean, running_var):
+def bn_finalize_partials(stats_partial, gamma, beta, eps, momentum, running_mean, running_var):
     """Per-tile conv partials -> (mean_invstd, scale_shift) in one launch (single-rank BatchNorm)."""
     lib = _lib.load()
     t, _, c = stats_partial.shape
     buf = torch.empty((4, c), dtype=torch.float32, device=stats_partial.device)
     mi, ss = buf[:2], buf[2:]
-    _lib.check(lib.semseg_bn_finalize_partials(_ptr(stats_partial), _ptr(tile_count), t, c, _ptr(gamma), _ptr(beta),
+    _lib.check(lib.semseg_bn_finalize_partials(_ptr(stats_partial), t, c, _ptr(gamma), _ptr(beta),
                                                float(eps), float(momentum), _ptr(running_mean), _ptr(running_var),
                                                _ptr(mi), _ptr(ss), _stream()), "semseg_bn_finalize_partials")
     return mi, ss
