@@ -271,11 +271,35 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch
     sc[q] = ss[c0 + q];
     sh[q] = ss[C + c0 + q];
   }
-  for (; idx < total; idx += stride) {
-    const long long p = idx / groups;
-    float f[8];
+  // stride is a multiple of groups, so pixel p advances by pstride each iteration; 4 pixels are kept in flight.
+  const long long pstride = stride / groups;
+  long long p = idx / groups;
+  constexpr int U = 4;
+  for (; p + (U - 1) * pstride < M; p += U * pstride) {
+    uint4 xv[U], rv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) xv[u] = *reinterpret_cast<const uint4*>(x + (p + u * pstride) * x_pitch + c0);
+    if (res) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) rv[u] = *reinterpret_cast<const uint4*>(res + (p + u * pstride) * res_pitch + c0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float f[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      unpack8(xv[u], f);
+      if (res) unpack8(rv[u], r);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float v = fmaf(f[q], sc[q], sh[q]) + r[q];
+        if (relu) v = fmaxf(v, 0.f);
+        f[q] = v;
+      }
+      *reinterpret_cast<uint4*>(y + (p + u * pstride) * y_pitch + c0) = pack8(f);
+    }
+  }
+  for (; p < M; p += pstride) {
+    float f[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), f);
-    float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (res) unpack8(*reinterpret_cast<const uint4*>(res + p * res_pitch + c0), r);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -310,7 +334,40 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
       mean[q] = mean_invstd[c0 + q];
       invstd[q] = mean_invstd[C + c0 + q];
     }
-    for (int r = r0 + pl; r < r1; r += 32) {
+    constexpr int U = 4;  // rows in flight per thread
+    int r = r0 + pl;
+    for (; r + (U - 1) * 32 < r1; r += U * 32) {
+      uint4 dv[U], xr[U], yr[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        dv[u] = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r + u * 32) * dy_pitch + c0);
+        xr[u] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r + u * 32) * x_pitch + c0);
+      }
+      if (relu) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          yr[u] = *reinterpret_cast<const uint4*>(y + static_cast<size_t>(r + u * 32) * y_pitch + c0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float d[8], xv[8];
+        unpack8(dv[u], d);
+        unpack8(xr[u], xv);
+        if (relu) {
+          float yv[8];
+          unpack8(yr[u], yv);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (!(yv[q] > 0.f)) d[q] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          a[q] += d[q];
+          b[q] = fmaf(d[q], (xv[q] - mean[q]) * invstd[q], b[q]);
+        }
+      }
+    }
+    for (; r < r1; r += 32) {
       float d[8], xv[8];
       unpack8(*reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * dy_pitch + c0), d);
       unpack8(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * x_pitch + c0), xv);
@@ -396,9 +453,40 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
     kx[q] = -ka[q] * invstd * sums[C + c] * inv_count;
     kb[q] = -ka[q] * sums[c] * inv_count - kx[q] * mean;
   }
-  for (; idx < total; idx += stride) {
-    const long long p = idx / groups;
-    float d[8], xv[8];
+  const long long pstride = stride / groups;
+  long long p = idx / groups;
+  constexpr int U = 4;
+  for (; p + (U - 1) * pstride < M; p += U * pstride) {
+    uint4 dv[U], xr[U], yr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      dv[u] = *reinterpret_cast<const uint4*>(dy + (p + u * pstride) * dy_pitch + c0);
+      xr[u] = *reinterpret_cast<const uint4*>(x + (p + u * pstride) * x_pitch + c0);
+    }
+    if (relu) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) yr[u] = *reinterpret_cast<const uint4*>(y + (p + u * pstride) * y_pitch + c0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float d[8], xv[8], o[8];
+      unpack8(dv[u], d);
+      unpack8(xr[u], xv);
+      if (relu) {
+        float yv[8];
+        unpack8(yr[u], yv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (!(yv[q] > 0.f)) d[q] = 0.f;
+      }
+      if (dres) *reinterpret_cast<uint4*>(dres + (p + u * pstride) * dres_pitch + c0) = pack8(d);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = fmaf(ka[q], d[q], fmaf(kx[q], xv[q], kb[q]));
+      *reinterpret_cast<uint4*>(dx + (p + u * pstride) * dx_pitch + c0) = pack8(o);
+    }
+  }
+  for (; p < M; p += pstride) {
+    float d[8], xv[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(dy + p * dy_pitch + c0), d);
     unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), xv);
     if (relu) {
@@ -409,7 +497,6 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
         if (!(yv[q] > 0.f)) d[q] = 0.f;
     }
     if (dres) *reinterpret_cast<uint4*>(dres + p * dres_pitch + c0) = pack8(d);
-    float o[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) o[q] = fmaf(ka[q], d[q], fmaf(kx[q], xv[q], kb[q]));
     *reinterpret_cast<uint4*>(dx + p * dx_pitch + c0) = pack8(o);

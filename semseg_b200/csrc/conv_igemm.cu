@@ -209,6 +209,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int ch = 0; ch < kChunks; ++ch) {
         const int c0 = n0 + ch * 64;  // first output channel of this chunk
         if (c0 >= p.Cout) break;      // (uniform) nothing to write for padded columns
+        // Prefetch this CTA's running statistics for the chunk's columns now; the read-modify-write below then
+        // does not expose the global-memory latency in the epilogue's critical path.
+        const bool do_stats = p.stats_partial != nullptr && p.epi_mode == SEMSEG_EPI_RAW;
+        float st_old[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float* st_dst = nullptr;
+        if (do_stats && et < 32) {
+          st_dst = p.stats_partial + static_cast<size_t>(blockIdx.x) * 3 * p.Cout + c0 + 2 * et;
+          st_old[0] = st_dst[0];
+          st_old[1] = st_dst[1];
+          st_old[2] = st_dst[p.Cout];
+          st_old[3] = st_dst[p.Cout + 1];
+          st_old[4] = st_dst[2 * p.Cout];
+          st_old[5] = st_dst[2 * p.Cout + 1];
+        }
         uint32_t v[2][32];
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(g * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N + ch * 64);
@@ -282,7 +296,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_store_commit();
         }
 
-        if (p.stats_partial != nullptr && p.epi_mode == SEMSEG_EPI_RAW) {
+        if (do_stats) {
           // Per-column statistics of the bf16 values just staged (exactly what BN-apply will read back).
           // Thread -> column pair cp (2 adjacent bf16 = one 4-byte word, conflict-free across the warp) and a
           // quarter of the rows; one pass accumulates sum and sum of squares, the four quarters are combined in
@@ -329,14 +343,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // Per-CTA running (sum, sum of squares, count) per column: this CTA is the only writer of its row and
             // a given column is always handled by the same thread, so plain read-modify-write is race free and
             // the accumulation order (this CTA's tile sequence) is fixed -> deterministic.
-            float* dst = p.stats_partial + static_cast<size_t>(blockIdx.x) * 3 * p.Cout;
-            const int col = c0 + 2 * cp;
-            dst[col] += S0;
-            dst[col + 1] += S1;
-            dst[p.Cout + col] += Q0;
-            dst[p.Cout + col + 1] += Q1;
-            dst[2 * p.Cout + col] += nt;
-            dst[2 * p.Cout + col + 1] += nt;
+            st_dst[0] = st_old[0] + S0;
+            st_dst[1] = st_old[1] + S1;
+            st_dst[p.Cout] = st_old[2] + Q0;
+            st_dst[p.Cout + 1] = st_old[3] + Q1;
+            st_dst[2 * p.Cout] = st_old[4] + nt;
+            st_dst[2 * p.Cout + 1] = st_old[5] + nt;
           }
           named_bar_sync(2, kEpiThreads);  // scratch may be rewritten by the next chunk
         }

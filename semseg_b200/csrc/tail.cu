@@ -132,149 +132,60 @@ __global__ void upsample_ce_reduce_kernel(const float* __restrict__ partial, int
 }
 
 // ---------------------------------------------------------------------------------------------------- backward
-constexpr int kOwnI = 3;   // owned node rows per CTA  -> 4 row intervals = 32 output rows
-constexpr int kOwnJ = 7;   // owned node cols per CTA  -> 8 col intervals = 64 output cols (2 warps per row)
-
-// block 256 threads = 8 warps. For each of the 4 row intervals (8 output rows): warp -> (row in interval r = warp>>1 ...)
-// see body. Shared: nodes [5][9][C], T [8 rows][7][C], acc [3][7][C].
+// Deterministic gather with one CTA per low-res node (n, i, j) and one thread per class: the node's gradient is
+//   dL[c] = sum over the <= 15 x 15 output pixels in its support of  wy * wx * (softmax_p[c] - [c == t_p]) * gs,
+// wy = 1 - |y - 8i|/8, wx = 1 - |x - 8j|/8. Every thread walks the support in the same fixed order, reading the
+// 3 x 3 node neighbourhood of its class from shared memory (conflict-free: consecutive classes) and the per-pixel
+// scalars (lse, target) as warp-uniform broadcasts. No atomics, no cross-thread reduction, each dlogits element is
+// written exactly once; the softmax of a pixel is recomputed by the (up to) four nodes that own it.
 __global__ void __launch_bounds__(256)
 upsample_ce_bwd_kernel(const float* __restrict__ logits, int pitch, int N, int h, int w, int C,
                        const long long* __restrict__ target, int Ho, int Wo, int ignore_index,
                        const float* __restrict__ lse, const float* __restrict__ loss_info,
                        const float* __restrict__ grad_out, float* __restrict__ dlogits) {
-  extern __shared__ float sm[];
-  float* S = sm;                          // [(kOwnI+2) * (kOwnJ+2)][C] node values; rows i0-1 .. i0+kOwnI
-  float* T = S + (kOwnI + 2) * (kOwnJ + 2) * C;  // [8][kOwnJ][C]
-  float* A = T + 8 * kOwnJ * C;           // [kOwnI][kOwnJ][C] accumulators
-  const int n = blockIdx.z;
-  const int i0 = blockIdx.y * kOwnI, j0 = blockIdx.x * kOwnJ;  // first owned node
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int SW = kOwnJ + 2;
-  for (int idx = tid; idx < (kOwnI + 2) * SW * C; idx += 256) {
-    const int c = idx % C;
+  extern __shared__ float S[];  // [3][3][C] node values around (i, j); out-of-range nodes are never read
+  const int j = blockIdx.x, i = blockIdx.y, n = blockIdx.z;
+  const int c = threadIdx.x;
+  for (int idx = threadIdx.x; idx < 9 * C; idx += blockDim.x) {
+    const int cc = idx % C;
     const int node = idx / C;
-    const int jj = node % SW, ii = node / SW;
-    const int gi = i0 - 1 + ii, gj = j0 - 1 + jj;
+    const int gi = i - 1 + node / 3, gj = j - 1 + node % 3;
     float v = 0.f;
     if (gi >= 0 && gi < h && gj >= 0 && gj < w)
-      v = logits[((static_cast<size_t>(n) * h + gi) * w + gj) * pitch + c];
+      v = logits[((static_cast<size_t>(n) * h + gi) * w + gj) * pitch + cc];
     S[idx] = v;
   }
-  for (int idx = tid; idx < kOwnI * kOwnJ * C; idx += 256) A[idx] = 0.f;
   __syncthreads();
+  if (c >= C) return;
   const float cntv = loss_info[1];
-  const float gscale = grad_out[0] / (cntv > 0.f ? cntv : 1.f);
-
-  // 4 row intervals q = 0..3 -> interval index iv = i0 - 1 + q, output rows y = 8*iv + r, r = 0..7.
-  // Within an interval, warps (2 per row) process rows r = warp>>1 (+4 on the second pass); half = warp&1 picks
-  // the 32-pixel half of the 64-pixel span: pixel x = 8*(j0-1) + half*32 + lane.
-#pragma unroll 1
-  for (int q = 0; q < kOwnI + 1; ++q) {
-    const int iv = i0 - 1 + q;
-    // T[r][jo][c] = sum_x Ww[x, j0+jo] * g[y, x, c]
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const int r = (warp >> 1) + pass * 4;
-      const int half = warp & 1;
-      const int y = 8 * iv + r;
-      const int x = 8 * (j0 - 1) + half * 32 + lane;
-      const bool pvalid = iv >= 0 && y < Ho && y >= 0 && x >= 0 && x < Wo;
-      // interpolation setup (clamped like ATen); node rows relative to S: (i - (i0-1))
-      const int yi0 = pvalid ? (y >> 3) : max(i0 - 1, 0);
-      const int yi1 = min(yi0 + 1, h - 1);
-      const float l1h = static_cast<float>(y & 7) * 0.125f, l0h = 1.f - l1h;
-      const int xj0 = pvalid ? (x >> 3) : max(j0 - 1, 0);
-      const int xj1 = min(xj0 + 1, w - 1);
+  const float gs = grad_out[0] / (cntv > 0.f ? cntv : 1.f);
+  const int y_lo = max(8 * i - 7, 0), y_hi = min(8 * i + 7, Ho - 1);
+  const int x_lo = max(8 * j - 7, 0), x_hi = min(8 * j + 7, Wo - 1);
+  float acc = 0.f;
+  for (int y = y_lo; y <= y_hi; ++y) {
+    const int i0 = y >> 3;
+    const int i1 = min(i0 + 1, h - 1);
+    const float l1h = static_cast<float>(y & 7) * 0.125f, l0h = 1.f - l1h;
+    const float wy = (i0 == i ? l0h : 0.f) + (i1 == i ? l1h : 0.f);
+    const float* r0 = S + (i0 - (i - 1)) * 3 * C + c;
+    const float* r1 = S + (i1 - (i - 1)) * 3 * C + c;
+    const size_t rowbase = (static_cast<size_t>(n) * Ho + y) * Wo;
+    float racc = 0.f;
+    for (int x = x_lo; x <= x_hi; ++x) {
+      const long long t = target[rowbase + x];
+      if (t == ignore_index || t < 0 || t >= C) continue;  // warp-uniform
+      const float ls = lse[rowbase + x];
+      const int j0 = x >> 3;
+      const int j1 = min(j0 + 1, w - 1);
       const float l1w = static_cast<float>(x & 7) * 0.125f, l0w = 1.f - l1w;
-      const float* r0 = S + ((yi0 - (i0 - 1)) * SW) * C;
-      const float* r1 = S + ((yi1 - (i0 - 1)) * SW) * C;
-      const int cj0 = (xj0 - (j0 - 1)) * C, cj1 = (xj1 - (j0 - 1)) * C;
-      float lsev = 0.f;
-      long long t = -1;
-      bool contributes = false;
-      if (pvalid) {
-        const size_t pix = (static_cast<size_t>(n) * Ho + y) * Wo + x;
-        t = target[pix];
-        lsev = lse[pix];
-        contributes = (t != ignore_index && t >= 0 && t < C);
-      }
-      // lane group = interval (x>>3); the group's left node is xj0, right node xj0+1.
-      // group index within this warp: lane>>3 (0..3); global interval column jv = (j0-1) + half*4 + (lane>>3).
-      const int grp = lane >> 3;
-      // KC classes per iteration: all shared-memory reads first, then the shuffle butterflies interleaved, then
-      // the stores (T/A alias S for the compiler, so without this the loop serialises on ~7 dependent shuffles).
-      constexpr int KC = 5;
-      float* stash = A + kOwnI * kOwnJ * C + r * C;
-      for (int cb = 0; cb < C; cb += KC) {
-        float a[KC], b[KC];
-#pragma unroll
-        for (int u = 0; u < KC; ++u) {
-          const int c = cb + u;
-          float g = 0.f;
-          if (contributes && c < C) {
-            const float v =
-                l0h * (l0w * r0[cj0 + c] + l1w * r0[cj1 + c]) + l1h * (l0w * r1[cj0 + c] + l1w * r1[cj1 + c]);
-            g = (__expf(v - lsev) - (c == t ? 1.f : 0.f)) * gscale;
-          }
-          a[u] = l0w * g;  // contribution to the left node of this pixel's interval
-          b[u] = l1w * g;  // ... and to the right node
-        }
-        // reduce inside the 8-lane interval group (fixed butterfly order -> deterministic)
-#pragma unroll
-        for (int o = 1; o <= 4; o <<= 1) {
-#pragma unroll
-          for (int u = 0; u < KC; ++u) {
-            a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
-            b[u] += __shfl_xor_sync(0xffffffffu, b[u], o);
-          }
-        }
-        float bp[KC];
-#pragma unroll
-        for (int u = 0; u < KC; ++u) bp[u] = __shfl_up_sync(0xffffffffu, b[u], 8);  // b of the previous group
-        // Interval group (half, grp) has left node jl = half*4 + grp - 1 (owned index). Owned node jo receives
-        // a(group with jl == jo) + b(group with jl == jo - 1); exactly one lane writes each T entry.
-        if ((lane & 7) == 0) {
-          const int jl = half * 4 + grp - 1;
-#pragma unroll
-          for (int u = 0; u < KC; ++u) {
-            const int c = cb + u;
-            if (c < C) {
-              if (grp >= 1) T[(r * kOwnJ + jl) * C + c] = a[u] + bp[u];
-              else if (half == 1) T[(r * kOwnJ + jl) * C + c] = a[u];  // + b of (half 0, grp 3): stashed below
-              if (half == 0 && grp == 3) stash[c] = b[u];              // cross-warp term for owned node 3
-            }
-          }
-        }
-      }
+      const float wx = (j0 == j ? l0w : 0.f) + (j1 == j ? l1w : 0.f);
+      const int o0 = (j0 - (j - 1)) * C, o1 = (j1 - (j - 1)) * C;
+      const float v = l0h * (l0w * r0[o0] + l1w * r0[o1]) + l1h * (l0w * r1[o0] + l1w * r1[o1]);
+      racc = fmaf(wx, __expf(v - ls) - (c == t ? 1.f : 0.f), racc);
     }
-    __syncthreads();
-    // node jo = 3 += stashed b of (half 0, group 3); then accumulate rows into A with the y weights, fixed order.
-    for (int idx = tid; idx < kOwnJ * C; idx += 256) {
-      const int c = idx % C;
-      const int jo = idx / C;
-      float acc_top = 0.f, acc_bot = 0.f;  // contributions to node row iv (weight l0h) and iv+1 (weight l1h)
-      for (int r = 0; r < 8; ++r) {
-        float tv = T[(r * kOwnJ + jo) * C + c];
-        if (jo == 3) tv += A[kOwnI * kOwnJ * C + r * C + c];
-        const float l1h = static_cast<float>(r) * 0.125f, l0h = 1.f - l1h;
-        acc_top += l0h * tv;
-        acc_bot += l1h * tv;
-      }
-      // interval iv: top node row = iv, bottom = iv+1 (owned rows are i0 .. i0+kOwnI-1)
-      const int top = iv - i0, bot = iv + 1 - i0;
-      if (top >= 0 && top < kOwnI) A[(top * kOwnJ + jo) * C + c] += acc_top;
-      if (bot >= 0 && bot < kOwnI) A[(bot * kOwnJ + jo) * C + c] += acc_bot;
-    }
-    __syncthreads();
+    acc = fmaf(wy, racc, acc);
   }
-  for (int idx = tid; idx < kOwnI * kOwnJ * C; idx += 256) {
-    const int c = idx % C;
-    const int node = idx / C;
-    const int jo = node % kOwnJ, io = node / kOwnJ;
-    const int gi = i0 + io, gj = j0 + jo;
-    if (gi < h && gj < w) dlogits[((static_cast<size_t>(n) * h + gi) * w + gj) * C + c] = A[idx];
-  }
+  dlogits[((static_cast<size_t>(n) * h + i) * w + j) * C + c] = acc * gs;
 }
 
 }  // namespace sb
@@ -325,18 +236,12 @@ extern "C" int semseg_upsample_ce_bwd(const float* logits, int pitch, int N, int
   int r = check_tail(logits, pitch, N, h, w, C, target, Ho, Wo);
   if (r) return r;
   SB_CHECK_ARG(lse && loss_info && grad_out && dlogits, "upsample_ce_bwd: null pointer");
-  dim3 grid(cdiv(w, kOwnJ), cdiv(h, kOwnI), N);
-  const size_t floats = static_cast<size_t>((kOwnI + 2) * (kOwnJ + 2) + 8 * kOwnJ + kOwnI * kOwnJ + 8) * C;
-  const size_t smem = floats * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    const int max_smem = ((kOwnI + 2) * (kOwnJ + 2) + 8 * kOwnJ + kOwnI * kOwnJ + 8) * kMaxClasses * (int)sizeof(float);
-    SB_CUDA(cudaFuncSetAttribute(upsample_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr = true;
-  }
-  upsample_ce_bwd_kernel<<<grid, 256, smem, stream>>>(logits, pitch, N, h, w, C,
-                                                     reinterpret_cast<const long long*>(target), Ho, Wo, ignore_index,
-                                                     lse, loss_info, grad_out, dlogits);
+  dim3 grid(w, h, N);
+  const int threads = (C + 31) / 32 * 32;
+  const size_t smem = static_cast<size_t>(9) * C * sizeof(float);
+  upsample_ce_bwd_kernel<<<grid, threads, smem, stream>>>(logits, pitch, N, h, w, C,
+                                                         reinterpret_cast<const long long*>(target), Ho, Wo,
+                                                         ignore_index, lse, loss_info, grad_out, dlogits);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
