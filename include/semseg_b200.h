@@ -215,15 +215,17 @@ int semseg_ppm_upsample_bwd(const void* dout, int dout_pitch, int c_off, void* c
  *   logits fp32 NHWC [N,h,w,C] (pitch), target int64 [N,Ho,Wo].
  *   fwd: loss_out[0] = mean CE, loss_out[1] = number of non-ignored pixels; argmax int64 [N,Ho,Wo] (or NULL);
  *        lse fp32 [N,Ho,Wo] (saved for backward); workspace: semseg_upsample_ce_workspace_floats() floats.
- *   bwd: dlogits fp32 [N,h,w,C] (dense, every element written) = grad_out[0] * d(mean CE)/dlogits.
+ *   bwd: dlogits fp32 [N,h,w,C] (dense, every element written) = grad_out[0] * d(mean CE)/dlogits;
+ *        workspace: semseg_upsample_ce_bwd_workspace_floats() floats (row-reduced intermediate [N][Ho][w][C]).
  */
 long long semseg_upsample_ce_workspace_floats(int N, int Ho, int Wo);
 int semseg_upsample_ce_fwd(const float* logits, int pitch, int N, int h, int w, int C, const int64_t* target,
                            int Ho, int Wo, int ignore_index, float* workspace, float* loss_out, int64_t* argmax,
                            float* lse, void* stream);
+long long semseg_upsample_ce_bwd_workspace_floats(int N, int Ho, int w, int C);
 int semseg_upsample_ce_bwd(const float* logits, int pitch, int N, int h, int w, int C, const int64_t* target,
                            int Ho, int Wo, int ignore_index, const float* lse, const float* loss_info,
-                           const float* grad_out, float* dlogits, void* stream);
+                           const float* grad_out, float* workspace, float* dlogits, void* stream);
 
 #ifdef __cplusplus
 }

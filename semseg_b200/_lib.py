@@ -95,8 +95,9 @@ SIGNATURES = {
     "semseg_upsample_ce_workspace_floats": (c_ll, [c_int, c_int, c_int]),
     "semseg_upsample_ce_fwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp,
                                        c_vp, c_vp, c_vp, c_vp]),
+    "semseg_upsample_ce_bwd_workspace_floats": (c_ll, [c_int, c_int, c_int, c_int]),
     "semseg_upsample_ce_bwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp,
-                                       c_vp, c_vp, c_vp, c_vp]),
+                                       c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

@@ -132,60 +132,82 @@ __global__ void upsample_ce_reduce_kernel(const float* __restrict__ partial, int
 }
 
 // ---------------------------------------------------------------------------------------------------- backward
-// Deterministic gather with one CTA per low-res node (n, i, j) and one thread per class: the node's gradient is
-//   dL[c] = sum over the <= 15 x 15 output pixels in its support of  wy * wx * (softmax_p[c] - [c == t_p]) * gs,
-// wy = 1 - |y - 8i|/8, wx = 1 - |x - 8j|/8. Every thread walks the support in the same fixed order, reading the
-// 3 x 3 node neighbourhood of its class from shared memory (conflict-free: consecutive classes) and the per-pixel
-// scalars (lse, target) as warp-uniform broadcasts. No atomics, no cross-thread reduction, each dlogits element is
-// written exactly once; the softmax of a pixel is recomputed by the (up to) four nodes that own it.
+// Separable, deterministic, no atomics:  dL[i,j,c] = gs * sum_y wy(y,i) * T[y,j,c],   T[y,j,c] = sum_x wx(x,j) g[y,x,c],
+// g[y,x,c] = softmax_{y,x}[c] - [c == t_{y,x}] (0 for ignored pixels).
+//
+// Phase 1 (rows): one CTA per output row (n, y), one thread per class. The thread walks x = 0..Wo-1; inside a
+// low-res interval the four node values of its class stay in registers, so a pixel costs ~12 FMA-class instructions
+// and one exp, no shared-memory traffic and no cross-lane reduction; lse / target of the row are staged in smem and
+// read as warp-uniform broadcasts. T is an fp32 workspace [N][Ho][w][C] (272 MB at bs16/150 classes).
+// Phase 2 (cols): one CTA per node row (n, i), threads over (j, c); fixed-order sum over the <= 15 rows in support.
 __global__ void __launch_bounds__(256)
-upsample_ce_bwd_kernel(const float* __restrict__ logits, int pitch, int N, int h, int w, int C,
-                       const long long* __restrict__ target, int Ho, int Wo, int ignore_index,
-                       const float* __restrict__ lse, const float* __restrict__ loss_info,
-                       const float* __restrict__ grad_out, float* __restrict__ dlogits) {
-  extern __shared__ float S[];  // [3][3][C] node values around (i, j); out-of-range nodes are never read
-  const int j = blockIdx.x, i = blockIdx.y, n = blockIdx.z;
-  const int c = threadIdx.x;
-  for (int idx = threadIdx.x; idx < 9 * C; idx += blockDim.x) {
-    const int cc = idx % C;
-    const int node = idx / C;
-    const int gi = i - 1 + node / 3, gj = j - 1 + node % 3;
-    float v = 0.f;
-    if (gi >= 0 && gi < h && gj >= 0 && gj < w)
-      v = logits[((static_cast<size_t>(n) * h + gi) * w + gj) * pitch + cc];
-    S[idx] = v;
+upsample_ce_bwd_rows_kernel(const float* __restrict__ logits, int pitch, int N, int h, int w, int C,
+                            const long long* __restrict__ target, int Ho, int Wo, int ignore_index,
+                            const float* __restrict__ lse, float* __restrict__ T) {
+  extern __shared__ float sm[];
+  float* s_lse = sm;                                   // [Wo]
+  int* s_t = reinterpret_cast<int*>(sm + Wo);          // [Wo], -1 = ignored
+  const int y = blockIdx.x, n = blockIdx.y;
+  const size_t rowbase = (static_cast<size_t>(n) * Ho + y) * Wo;
+  for (int x = threadIdx.x; x < Wo; x += blockDim.x) {
+    const long long t = target[rowbase + x];
+    s_t[x] = (t == ignore_index || t < 0 || t >= C) ? -1 : static_cast<int>(t);
+    s_lse[x] = lse[rowbase + x];
   }
   __syncthreads();
+  const int c = threadIdx.x;
   if (c >= C) return;
+  const int i0 = y >> 3;
+  const int i1 = min(i0 + 1, h - 1);
+  const float l1h = static_cast<float>(y & 7) * 0.125f, l0h = 1.f - l1h;
+  const float* L0 = logits + (static_cast<size_t>(n) * h + i0) * w * pitch + c;
+  const float* L1 = logits + (static_cast<size_t>(n) * h + i1) * w * pitch + c;
+  float* Trow = T + ((static_cast<size_t>(n) * Ho + y) * w) * C + c;
+  float a = L0[0], cc = L1[0];      // left node column of the current interval (rows i0 / i1)
+  float nb = L0[static_cast<size_t>(min(1, w - 1)) * pitch], nd = L1[static_cast<size_t>(min(1, w - 1)) * pitch];
+  float carry = 0.f;                // right-node contribution of the previous interval
+  for (int j0 = 0; j0 < w; ++j0) {
+    const float b = nb, d = nd;     // right node column (j1 = min(j0+1, w-1))
+    const int jn = min(j0 + 2, w - 1);
+    nb = L0[static_cast<size_t>(jn) * pitch];          // prefetch the next interval's right column
+    nd = L1[static_cast<size_t>(jn) * pitch];
+    float accL = 0.f, accR = 0.f;
+    const int xb = j0 * 8;
+    const int xe = min(xb + 8, Wo);
+#pragma unroll 8
+    for (int x = xb; x < xe; ++x) {
+      const int t = s_t[x];
+      if (t < 0) continue;  // warp-uniform
+      const float l1w = static_cast<float>(x & 7) * 0.125f, l0w = 1.f - l1w;
+      const float v = l0h * (l0w * a + l1w * b) + l1h * (l0w * cc + l1w * d);
+      const float g = __expf(v - s_lse[x]) - (c == t ? 1.f : 0.f);
+      accL = fmaf(l0w, g, accL);
+      accR = fmaf(l1w, g, accR);
+    }
+    Trow[static_cast<size_t>(j0) * C] = carry + accL;
+    carry = accR;
+    a = b;
+    cc = d;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+upsample_ce_bwd_cols_kernel(const float* __restrict__ T, int N, int h, int w, int C, int Ho,
+                            const float* __restrict__ loss_info, const float* __restrict__ grad_out,
+                            float* __restrict__ dlogits) {
+  const int i = blockIdx.x, n = blockIdx.y;
   const float cntv = loss_info[1];
   const float gs = grad_out[0] / (cntv > 0.f ? cntv : 1.f);
   const int y_lo = max(8 * i - 7, 0), y_hi = min(8 * i + 7, Ho - 1);
-  const int x_lo = max(8 * j - 7, 0), x_hi = min(8 * j + 7, Wo - 1);
-  float acc = 0.f;
-  for (int y = y_lo; y <= y_hi; ++y) {
-    const int i0 = y >> 3;
-    const int i1 = min(i0 + 1, h - 1);
-    const float l1h = static_cast<float>(y & 7) * 0.125f, l0h = 1.f - l1h;
-    const float wy = (i0 == i ? l0h : 0.f) + (i1 == i ? l1h : 0.f);
-    const float* r0 = S + (i0 - (i - 1)) * 3 * C + c;
-    const float* r1 = S + (i1 - (i - 1)) * 3 * C + c;
-    const size_t rowbase = (static_cast<size_t>(n) * Ho + y) * Wo;
-    float racc = 0.f;
-    for (int x = x_lo; x <= x_hi; ++x) {
-      const long long t = target[rowbase + x];
-      if (t == ignore_index || t < 0 || t >= C) continue;  // warp-uniform
-      const float ls = lse[rowbase + x];
-      const int j0 = x >> 3;
-      const int j1 = min(j0 + 1, w - 1);
-      const float l1w = static_cast<float>(x & 7) * 0.125f, l0w = 1.f - l1w;
-      const float wx = (j0 == j ? l0w : 0.f) + (j1 == j ? l1w : 0.f);
-      const int o0 = (j0 - (j - 1)) * C, o1 = (j1 - (j - 1)) * C;
-      const float v = l0h * (l0w * r0[o0] + l1w * r0[o1]) + l1h * (l0w * r1[o0] + l1w * r1[o1]);
-      racc = fmaf(wx, __expf(v - ls) - (c == t ? 1.f : 0.f), racc);
+  const int wc = w * C;
+  for (int idx = threadIdx.x; idx < wc; idx += blockDim.x) {
+    float acc = 0.f;
+    for (int y = y_lo; y <= y_hi; ++y) {
+      const float wy = 1.f - static_cast<float>(abs(y - 8 * i)) * 0.125f;
+      acc = fmaf(wy, T[(static_cast<size_t>(n) * Ho + y) * wc + idx], acc);
     }
-    acc = fmaf(wy, racc, acc);
+    dlogits[(static_cast<size_t>(n) * h + i) * wc + idx] = acc * gs;
   }
-  dlogits[((static_cast<size_t>(n) * h + i) * w + j) * C + c] = acc * gs;
 }
 
 }  // namespace sb
@@ -229,19 +251,24 @@ extern "C" int semseg_upsample_ce_fwd(const float* logits, int pitch, int N, int
   return SEMSEG_OK;
 }
 
+extern "C" long long semseg_upsample_ce_bwd_workspace_floats(int N, int Ho, int w, int C) {
+  return static_cast<long long>(N) * Ho * w * C;
+}
+
 extern "C" int semseg_upsample_ce_bwd(const float* logits, int pitch, int N, int h, int w, int C,
                                       const int64_t* target, int Ho, int Wo, int ignore_index, const float* lse,
-                                      const float* loss_info, const float* grad_out, float* dlogits, void* stream_) {
+                                      const float* loss_info, const float* grad_out, float* workspace,
+                                      float* dlogits, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int r = check_tail(logits, pitch, N, h, w, C, target, Ho, Wo);
   if (r) return r;
-  SB_CHECK_ARG(lse && loss_info && grad_out && dlogits, "upsample_ce_bwd: null pointer");
-  dim3 grid(w, h, N);
+  SB_CHECK_ARG(lse && loss_info && grad_out && dlogits && workspace, "upsample_ce_bwd: null pointer");
   const int threads = (C + 31) / 32 * 32;
-  const size_t smem = static_cast<size_t>(9) * C * sizeof(float);
-  upsample_ce_bwd_kernel<<<grid, threads, smem, stream>>>(logits, pitch, N, h, w, C,
-                                                         reinterpret_cast<const long long*>(target), Ho, Wo,
-                                                         ignore_index, lse, loss_info, grad_out, dlogits);
+  const size_t smem = static_cast<size_t>(Wo) * 8;
+  upsample_ce_bwd_rows_kernel<<<dim3(Ho, N), threads, smem, stream>>>(
+      logits, pitch, N, h, w, C, reinterpret_cast<const long long*>(target), Ho, Wo, ignore_index, lse, workspace);
+  SB_LAUNCHED();
+  upsample_ce_bwd_cols_kernel<<<dim3(h, N), 256, 0, stream>>>(workspace, N, h, w, C, Ho, loss_info, grad_out, dlogits);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }

@@ -388,9 +388,12 @@ def upsample_ce_bwd(logits, target, ignore_index, lse, info, grad_out):
     n, h, w, c = logits.shape
     _, ho, wo = target.shape
     dl = torch.empty((n, h, w, c), dtype=torch.float32, device=logits.device)
+    ws = torch.empty((int(lib.semseg_upsample_ce_bwd_workspace_floats(n, ho, w, c)),), dtype=torch.float32,
+                     device=logits.device)
     g = grad_out.reshape(1).float().contiguous()
     _lib.check(lib.semseg_upsample_ce_bwd(_ptr(logits), logits.stride(2), n, h, w, c, _ptr(target), ho, wo,
-                                          int(ignore_index), _ptr(lse), _ptr(info), _ptr(g), _ptr(dl), _stream()),
+                                          int(ignore_index), _ptr(lse), _ptr(info), _ptr(g), _ptr(ws), _ptr(dl),
+                                          _stream()),
                "semseg_upsample_ce_bwd")
     return dl
 
