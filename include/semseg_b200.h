@@ -191,6 +191,14 @@ int semseg_add_bf16(const void* a, int a_pitch, const void* b, int b_pitch, void
                     int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC bf16 (model/resnet.py:115): y [N,Ho,Wo,C] with
+ * Ho = (H-1)/2+1. Backward re-derives the arg-max (first maximum in window order, as ATen) and gathers:
+ * dx [N,H,W,C] dense, deterministic, no index tensor.
+ */
+int semseg_maxpool3x3s2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int semseg_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Pyramid pooling module data movement (model/pspnet.py:12-26), NHWC bf16, all bins in one launch.
  *   bins[nb] = pooled sizes (1,2,3,6); per-bin tensors are [N][b][b][channels] contiguous bf16.
  *   ppm_pool            : pooled_k = AdaptiveAvgPool2d(b_k)(x), window [floor(i*H/b), ceil((i+1)*H/b)).

@@ -455,7 +455,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
   }
   const long long pstride = stride / groups;
   long long p = idx / groups;
-  constexpr int U = 4;
+  constexpr int U = 2;
   for (; p + (U - 1) * pstride < M; p += U * pstride) {
     uint4 dv[U], xr[U], yr[U];
 #pragma unroll

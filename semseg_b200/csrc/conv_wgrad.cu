@@ -20,26 +20,35 @@ constexpr int kWgThreads = 192;
 constexpr int kWgEpiThreads = 128;
 constexpr int kWgBoxPixels = 64;
 constexpr int kWgBoxBytes = kWgBoxPixels * 128;  // one 64-channel x 64-pixel box
-constexpr int kWgBlockN = 256;
 constexpr int kWgABoxes = 2;                      // 128 Cout channels
-constexpr int kWgBBoxes = kWgBlockN / 64;         // 256 Cin channels
-constexpr int kWgStageBytes = (kWgABoxes + kWgBBoxes) * kWgBoxBytes;  // 48 KB
-constexpr int kWgStages = 4;
-constexpr int kWgTmemCols = 2 * kWgBlockN;
-constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 1024;
+
+// N tile (Cin channels per work unit): 256 for wide layers, 128 / 64 for the narrow ones (stem, layer1/2).
+template <int BN>
+struct WgCfg {
+  static constexpr int kBBoxes = BN / 64;
+  static constexpr int kStageBytes = (kWgABoxes + kBBoxes) * kWgBoxBytes;  // 48 / 32 / 24 KB
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+};
 
 struct WgradKParams {
   int N, H, W, Cin, Cout, taps;
   int bh, bw, tiles_h, tiles_w, num_boxes;
-  int co_tiles, ci_tiles, n_splits, boxes_per_split;
+  int co_tiles, ci_tiles, n_splits, boxes_per_split, block_n;
   int dh[SEMSEG_MAX_TAPS], dw[SEMSEG_MAX_TAPS], img_add[SEMSEG_MAX_TAPS];
   int img_mul;
   float* out;  // [n_splits][taps][Cout][Cin]
 };
 
+template <int kWgBlockN>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                   const WgradKParams p) {
+  constexpr int kWgBBoxes = WgCfg<kWgBlockN>::kBBoxes;
+  constexpr int kWgStageBytes = WgCfg<kWgBlockN>::kStageBytes;
+  constexpr int kWgStages = WgCfg<kWgBlockN>::kStages;
+  constexpr int kWgTmemCols = WgCfg<kWgBlockN>::kTmemCols;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* misc = smem + kWgStages * kWgStageBytes;
@@ -222,6 +231,19 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int n_splits
   }
 }
 
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradKParams& kp, int grid,
+                        cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 WgCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  conv_wgrad_kernel<BN><<<grid, kWgThreads, WgCfg<BN>::kSmemBytes, stream>>>(tmDY, tmX, kp);
+  return SEMSEG_OK;
+}
+
 static void wgrad_geometry(const semseg_wgrad_desc* d, WgradKParams* kp) {
   kp->N = d->N; kp->H = d->H; kp->W = d->W; kp->Cin = d->Cin; kp->Cout = d->Cout; kp->taps = d->taps;
   choose_box(d->H, d->W, kWgBoxPixels, &kp->bh, &kp->bw);
@@ -229,7 +251,8 @@ static void wgrad_geometry(const semseg_wgrad_desc* d, WgradKParams* kp) {
   kp->tiles_w = cdiv(d->W, kp->bw);
   kp->num_boxes = d->N * kp->tiles_h * kp->tiles_w;
   kp->co_tiles = cdiv(d->Cout, 128);
-  kp->ci_tiles = cdiv(d->Cin, kWgBlockN);
+  kp->block_n = d->Cin > 128 ? 256 : (d->Cin > 64 ? 128 : 64);
+  kp->ci_tiles = cdiv(d->Cin, kp->block_n);
   const int units = d->taps * kp->co_tiles * kp->ci_tiles;
   int splits = d->n_splits;
   if (splits <= 0) {
@@ -291,14 +314,15 @@ extern "C" int semseg_conv_wgrad(const semseg_wgrad_desc* d, void* stream_) {
     int r = encode_tmap_bf16(&tmX, d->x, 4, dims, str, box);
     if (r) return r;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
-    attr_set = true;
-  }
   const int units = kp.taps * kp.co_tiles * kp.ci_tiles * kp.n_splits;
   const int grid = units < num_sms() ? units : num_sms();
-  conv_wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(tmDY, tmX, kp);
+  int rc = SEMSEG_OK;
+  switch (kp.block_n) {
+    case 256: rc = launch_wgrad<256>(tmDY, tmX, kp, grid, stream); break;
+    case 128: rc = launch_wgrad<128>(tmDY, tmX, kp, grid, stream); break;
+    default: rc = launch_wgrad<64>(tmDY, tmX, kp, grid, stream); break;
+  }
+  if (rc) return rc;
   SB_LAUNCHED();
   return SEMSEG_OK;
 }

@@ -1,0 +1,149 @@
+// MaxPool2d(kernel 3, stride 2, padding 1) on NHWC bf16 (model/resnet.py:115, used as layer0[9]).
+// Forward: one thread per (output pixel, 8 channels). Backward is a deterministic gather: every input pixel
+// re-derives, for the (up to four) windows that contain it, whether it is that window's arg-max (first maximum in
+// row-major window order, the tie rule of ATen's max_pool2d_with_indices) and sums the matching dy. No index tensor,
+// no atomics, every dx element written once.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace sb {
+
+__device__ __forceinline__ void mp_ld8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 t = __bfloat1622float2(h[q]);
+    f[2 * q] = t.x;
+    f[2 * q + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void mp_st8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+__global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
+                                        int H, int W, int C, int Ho, int Wo) {
+  const int groups = C >> 3;
+  const long long total = static_cast<long long>(N) * Ho * Wo * groups;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(idx % groups) << 3;
+    long long p = idx / groups;
+    const int wo = static_cast<int>(p % Wo);
+    p /= Wo;
+    const int ho = static_cast<int>(p % Ho);
+    const int n = static_cast<int>(p / Ho);
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = 2 * ho - 1 + kh;
+      if (h < 0 || h >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = 2 * wo - 1 + kw;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        mp_ld8(x + ((static_cast<size_t>(n) * H + h) * W + w) * C + c0, f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], f[q]);
+      }
+    }
+    mp_st8(y + ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c0, m);
+  }
+}
+
+__global__ void maxpool3x3s2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                        __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
+  const int groups = C >> 3;
+  const long long total = static_cast<long long>(N) * H * W * groups;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(idx % groups) << 3;
+    long long p = idx / groups;
+    const int w = static_cast<int>(p % W);
+    p /= W;
+    const int h = static_cast<int>(p % H);
+    const int n = static_cast<int>(p / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // windows containing (h, w): ho with 2*ho-1 <= h <= 2*ho+1
+    const int ho_lo = max((h) / 2, 0), ho_hi = min((h + 1) / 2, Ho - 1);
+    const int wo_lo = max((w) / 2, 0), wo_hi = min((w + 1) / 2, Wo - 1);
+    const __nv_bfloat16* xn = x + static_cast<size_t>(n) * H * W * C + c0;
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        // first maximum in row-major order over the valid window positions
+        float best[8];
+        int arg[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          best[q] = -INFINITY;
+          arg[q] = -1;
+        }
+        for (int kh = 0; kh < 3; ++kh) {
+          const int hh = 2 * ho - 1 + kh;
+          if (hh < 0 || hh >= H) continue;
+          for (int kw = 0; kw < 3; ++kw) {
+            const int ww = 2 * wo - 1 + kw;
+            if (ww < 0 || ww >= W) continue;
+            float f[8];
+            mp_ld8(xn + (static_cast<size_t>(hh) * W + ww) * C, f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (f[q] > best[q] || arg[q] < 0) {
+                best[q] = f[q];
+                arg[q] = hh * W + ww;
+              }
+            }
+          }
+        }
+        float g[8];
+        mp_ld8(dy + ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c0, g);
+        const int me = h * W + w;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (arg[q] == me) acc[q] += g[q];
+      }
+    }
+    mp_st8(dx + ((static_cast<size_t>(n) * H + h) * W + w) * C + c0, acc);
+  }
+}
+
+static int mp_blocks(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int semseg_maxpool3x3s2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool_fwd: bad args");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
+  maxpool3x3s2_fwd_kernel<<<mp_blocks(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
+                                                               static_cast<__nv_bfloat16*>(y), N, H, W, C, Ho, Wo);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C,
+                                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(x && dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool_bwd: bad args");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(N) * H * W * (C / 8);
+  maxpool3x3s2_bwd_kernel<<<mp_blocks(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
+                                                               static_cast<const __nv_bfloat16*>(dy),
+                                                               static_cast<__nv_bfloat16*>(dx), N, H, W, C, Ho, Wo);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}

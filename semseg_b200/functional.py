@@ -312,7 +312,26 @@ def dropout2d_nhwc(x, p, training):
     return x * (keep / (1.0 - p)).to(x.dtype)
 
 
+class _MaxPool3x3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.maxpool3x3s2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.maxpool3x3s2_bwd(x, dy)
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
 def maxpool_nhwc(x, pool):
+    if (_pair(pool.kernel_size) == (3, 3) and _pair(pool.stride) == (2, 2) and _pair(pool.padding) == (1, 1)
+            and _pair(pool.dilation) == (1, 1) and not pool.ceil_mode and x.shape[-1] % 8 == 0):
+        return _MaxPool3x3s2.apply(x)
     xn = x.permute(0, 3, 1, 2)
     y = F.max_pool2d(xn, pool.kernel_size, pool.stride, pool.padding, pool.dilation, pool.ceil_mode)
     return y.permute(0, 2, 3, 1).contiguous()

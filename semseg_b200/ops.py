@@ -447,3 +447,24 @@ def ppm_upsample_bwd(dout, c_off, bins, cr):
     _lib.check(lib.semseg_ppm_upsample_bwd(_ptr(dout), p, c_off, parr, barr, nb, n, h, w, cr, _stream()),
                "semseg_ppm_upsample_bwd")
     return dfeats
+
+
+# ------------------------------------------------------------------------------------------------ max pool
+def maxpool3x3s2_fwd(x):
+    _require_cuda(x)
+    lib = _lib.load()
+    n, h, w, c, p = _nhwc_meta(x)
+    assert p == c, "maxpool expects a dense NHWC tensor"
+    y = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.semseg_maxpool3x3s2_fwd(_ptr(x), _ptr(y), n, h, w, c, _stream()), "semseg_maxpool3x3s2_fwd")
+    return y
+
+
+def maxpool3x3s2_bwd(x, dy):
+    lib = _lib.load()
+    n, h, w, c, _ = _nhwc_meta(x)
+    dy = dy.contiguous()
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.semseg_maxpool3x3s2_bwd(_ptr(x), _ptr(dy), _ptr(dx), n, h, w, c, _stream()),
+               "semseg_maxpool3x3s2_bwd")
+    return dx

@@ -257,6 +257,22 @@ def test_ppm_kernels_vs_torch(shape):
         assert util.rel_l2(f.grad, r.grad.permute(0, 2, 3, 1)) < 6e-3
 
 
+def test_maxpool_vs_torch_with_ties():
+    """3x3/s2/p1 max-pool; inputs are post-ReLU (many exact ties at 0) so the arg-max tie rule is exercised."""
+    from semseg_b200 import functional as SF
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (n, h, w, c) in [(2, 237, 237, 128), (1, 9, 12, 64), (2, 8, 8, 8)]:
+        x = torch.relu(torch.randn((n, h, w, c), device="cuda", generator=g)).to(torch.bfloat16).requires_grad_(True)
+        y = SF.maxpool_nhwc(x, torch.nn.MaxPool2d(3, 2, 1))
+        xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+        yr = F.max_pool2d(xr, 3, 2, 1)
+        assert torch.equal(y.float(), yr.permute(0, 2, 3, 1))
+        gy = torch.randn(y.shape, device="cuda", generator=g).to(torch.bfloat16)
+        y.backward(gy)
+        yr.backward(gy.float().permute(0, 3, 1, 2))
+        assert util.rel_l2(x.grad, xr.grad.permute(0, 2, 3, 1)) < 4e-3     # bf16 rounding of summed gradients only
+
+
 # ------------------------------------------------------------------------------------------------ blocks
 def _grad_check(model_params, oracle_sd, names, tol):
     bad = []
