@@ -172,15 +172,17 @@ int semseg_bn_fold_eval(const float* gamma, const float* beta, const float* runn
 int semseg_bn_apply(const void* x, int x_pitch, const float* scale_shift, const void* residual, int res_pitch,
                     void* y, int y_pitch, int M, int C, int relu, void* stream);
 /* Backward reduce: with dz = dy * (y > 0 if relu) and xhat = (x - mean)*invstd,
- *   sums [2][C] = (sum dz, sum dz*xhat). y may be NULL when relu == 0. */
+ *   sums [2][C] = (sum dz, sum dz*xhat). y may be NULL when relu == 0; when relu != 0 and y == NULL the mask is
+ *   recomputed as fma(x, scale, shift) > 0 from scale_shift [2][C] (valid when the forward had no residual). */
 int semseg_bn_bwd_reduce(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x, int x_pitch,
-                         const float* mean_invstd, int M, int C, int relu, float* workspace,
+                         const float* mean_invstd, const float* scale_shift, int M, int C, int relu, float* workspace,
                          long long workspace_floats, float* sums, void* stream);
 /* Backward apply: dx = gamma*invstd*(dz - sum_dz/count - xhat*sum_dzxhat/count) (bf16);
  *   dres (optional) = dz (bf16); dgamma = sum_dzxhat, dbeta = sum_dz written to dgamma_dbeta [2][C].
  *   count = total number of samples per channel across all ranks. */
 int semseg_bn_bwd_apply(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x, int x_pitch,
-                        const float* mean_invstd, const float* gamma, const float* sums, float count, int M,
+                        const float* mean_invstd, const float* gamma, const float* scale_shift, const float* sums,
+                        float count, int M,
                         int C, int relu, void* dx, int dx_pitch, void* dres, int dres_pitch,
                         float* dgamma_dbeta, void* stream);
 /* dz = dy * (y > 0); plain ReLU backward for tensors without BN in between. */

@@ -81,9 +81,9 @@ SIGNATURES = {
     "semseg_bn_finalize_partials": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "semseg_bn_fold_eval": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_vp, c_vp]),
     "semseg_bn_apply": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
-    "semseg_bn_bwd_reduce": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp, c_ll,
-                                     c_vp, c_vp]),
-    "semseg_bn_bwd_apply": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_f, c_int, c_int,
+    "semseg_bn_bwd_reduce": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp,
+                                     c_ll, c_vp, c_vp]),
+    "semseg_bn_bwd_apply": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_int,
                                     c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     "semseg_relu_bwd": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp]),
     "semseg_add_bf16": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp]),

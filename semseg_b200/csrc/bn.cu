@@ -315,8 +315,8 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pitch,
                                      const __nv_bfloat16* __restrict__ y, int y_pitch,
                                      const __nv_bfloat16* __restrict__ x, int x_pitch,
-                                     const float* __restrict__ mean_invstd, int M, int C, int relu,
-                                     int rows_per_chunk, float* __restrict__ part) {
+                                     const float* __restrict__ mean_invstd, const float* __restrict__ ss, int M,
+                                     int C, int relu, int rows_per_chunk, float* __restrict__ part) {
   __shared__ float s_a[32][65];
   __shared__ float s_b[32][65];
   const int gl = threadIdx.x & 7;
@@ -328,12 +328,16 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
   const bool active = c0 < C;
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (active) {
-    float mean[8], invstd[8];
+    float mean[8], invstd[8], msc[8], msh[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       mean[q] = mean_invstd[c0 + q];
       invstd[q] = mean_invstd[C + c0 + q];
+      msc[q] = ss ? ss[c0 + q] : 0.f;       // ReLU mask recomputed from the raw conv output when y is not given:
+      msh[q] = ss ? ss[C + c0 + q] : 0.f;   // y > 0  <=>  fma(x, scale, shift) > 0 (same fma as bn_apply, no residual)
     }
+    const bool mask_from_y = relu && y != nullptr;
+    const bool mask_from_x = relu && y == nullptr;
     constexpr int U = 4;  // rows in flight per thread
     int r = r0 + pl;
     for (; r + (U - 1) * 32 < r1; r += U * 32) {
@@ -343,7 +347,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
         dv[u] = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r + u * 32) * dy_pitch + c0);
         xr[u] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r + u * 32) * x_pitch + c0);
       }
-      if (relu) {
+      if (mask_from_y) {
 #pragma unroll
         for (int u = 0; u < U; ++u)
           yr[u] = *reinterpret_cast<const uint4*>(y + static_cast<size_t>(r + u * 32) * y_pitch + c0);
@@ -353,12 +357,16 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
         float d[8], xv[8];
         unpack8(dv[u], d);
         unpack8(xr[u], xv);
-        if (relu) {
+        if (mask_from_y) {
           float yv[8];
           unpack8(yr[u], yv);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             if (!(yv[q] > 0.f)) d[q] = 0.f;
+        } else if (mask_from_x) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (!(fmaf(xv[q], msc[q], msh[q]) > 0.f)) d[q] = 0.f;
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -371,12 +379,16 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
       float d[8], xv[8];
       unpack8(*reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * dy_pitch + c0), d);
       unpack8(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * x_pitch + c0), xv);
-      if (relu) {
+      if (mask_from_y) {
         float yv[8];
         unpack8(*reinterpret_cast<const uint4*>(y + static_cast<size_t>(r) * y_pitch + c0), yv);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           if (!(yv[q] > 0.f)) d[q] = 0.f;
+      } else if (mask_from_x) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (!(fmaf(xv[q], msc[q], msh[q]) > 0.f)) d[q] = 0.f;
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -428,7 +440,8 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
                                     const __nv_bfloat16* __restrict__ y, int y_pitch,
                                     const __nv_bfloat16* __restrict__ x, int x_pitch,
                                     const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ sums, float inv_count, long long M, int C, int relu,
+                                    const float* __restrict__ ss, const float* __restrict__ sums, float inv_count,
+                                    long long M, int C, int relu,
                                     __nv_bfloat16* __restrict__ dx, int dx_pitch, __nv_bfloat16* __restrict__ dres,
                                     int dres_pitch, float* __restrict__ dgamma_dbeta) {
   const int groups = C >> 3;
@@ -443,10 +456,14 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const int c0 = static_cast<int>(idx % groups) << 3;
   // dx = g*invstd*(dz - s1/M - xhat*s2/M) = ka*dz + kx*x + kb  with xhat = (x - mean)*invstd
-  float ka[8], kx[8], kb[8];
+  float ka[8], kx[8], kb[8], msc[8], msh[8];
+  const bool mask_from_y = relu && y != nullptr;
+  const bool mask_from_x = relu && y == nullptr;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int c = c0 + q;
+    msc[q] = ss ? ss[c] : 0.f;
+    msh[q] = ss ? ss[C + c] : 0.f;
     const float mean = mean_invstd[c], invstd = mean_invstd[C + c];
     const float g = gamma ? gamma[c] : 1.f;
     ka[q] = g * invstd;
@@ -463,7 +480,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
       dv[u] = *reinterpret_cast<const uint4*>(dy + (p + u * pstride) * dy_pitch + c0);
       xr[u] = *reinterpret_cast<const uint4*>(x + (p + u * pstride) * x_pitch + c0);
     }
-    if (relu) {
+    if (mask_from_y) {
 #pragma unroll
       for (int u = 0; u < U; ++u) yr[u] = *reinterpret_cast<const uint4*>(y + (p + u * pstride) * y_pitch + c0);
     }
@@ -472,12 +489,16 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
       float d[8], xv[8], o[8];
       unpack8(dv[u], d);
       unpack8(xr[u], xv);
-      if (relu) {
+      if (mask_from_y) {
         float yv[8];
         unpack8(yr[u], yv);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           if (!(yv[q] > 0.f)) d[q] = 0.f;
+      } else if (mask_from_x) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (!(fmaf(xv[q], msc[q], msh[q]) > 0.f)) d[q] = 0.f;
       }
       if (dres) *reinterpret_cast<uint4*>(dres + (p + u * pstride) * dres_pitch + c0) = pack8(d);
 #pragma unroll
@@ -489,12 +510,16 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
     float d[8], xv[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(dy + p * dy_pitch + c0), d);
     unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), xv);
-    if (relu) {
+    if (mask_from_y) {
       float yv[8];
       unpack8(*reinterpret_cast<const uint4*>(y + p * y_pitch + c0), yv);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         if (!(yv[q] > 0.f)) d[q] = 0.f;
+    } else if (mask_from_x) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (!(fmaf(xv[q], msc[q], msh[q]) > 0.f)) d[q] = 0.f;
     }
     if (dres) *reinterpret_cast<uint4*>(dres + p * dres_pitch + c0) = pack8(d);
 #pragma unroll
@@ -650,20 +675,21 @@ extern "C" int semseg_bn_apply(const void* x, int x_pitch, const float* scale_sh
 }
 
 extern "C" int semseg_bn_bwd_reduce(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x,
-                                    int x_pitch, const float* mean_invstd, int M, int C, int relu, float* workspace,
+                                    int x_pitch, const float* mean_invstd, const float* scale_shift, int M, int C,
+                                    int relu, float* workspace,
                                     long long workspace_floats, float* sums, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(dy && x && mean_invstd && workspace && sums && M > 0 && C > 0, "bn_bwd_reduce: bad args");
-  SB_CHECK_ARG(!relu || y, "bn_bwd_reduce: relu needs y");
-  SB_CHECK_ARG(C % 8 == 0 && dy_pitch % 8 == 0 && x_pitch % 8 == 0 && (!relu || y_pitch % 8 == 0),
+  SB_CHECK_ARG(!relu || y || scale_shift, "bn_bwd_reduce: relu needs y or scale_shift");
+  SB_CHECK_ARG(C % 8 == 0 && dy_pitch % 8 == 0 && x_pitch % 8 == 0 && (!(relu && y) || y_pitch % 8 == 0),
                "bn_bwd_reduce: channels and pitches must be multiples of 8");
   SB_CHECK_ARG(workspace_floats >= semseg_bn_workspace_floats(M, C), "bn_bwd_reduce: workspace too small");
   const int rows = chunk_rows(M);
   const int chunks = cdiv(M, rows);
   dim3 grid(cdiv(C, 64), chunks);
   bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_pitch, static_cast<const bf16*>(y),
-                                                 y_pitch, static_cast<const bf16*>(x), x_pitch, mean_invstd, M, C,
-                                                 relu, rows, workspace);
+                                                 y_pitch, static_cast<const bf16*>(x), x_pitch, mean_invstd,
+                                                 scale_shift, M, C, relu, rows, workspace);
   SB_LAUNCHED();
   bn_bwd_reduce_final_kernel<<<cdiv(2 * C, 32), 1024, 0, stream>>>(workspace, chunks, C, sums);
   SB_LAUNCHED();
@@ -671,19 +697,20 @@ extern "C" int semseg_bn_bwd_reduce(const void* dy, int dy_pitch, const void* y,
 }
 
 extern "C" int semseg_bn_bwd_apply(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x,
-                                   int x_pitch, const float* mean_invstd, const float* gamma, const float* sums,
+                                   int x_pitch, const float* mean_invstd, const float* gamma,
+                                   const float* scale_shift, const float* sums,
                                    float count, int M, int C, int relu, void* dx, int dx_pitch, void* dres,
                                    int dres_pitch, float* dgamma_dbeta, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(dy && x && mean_invstd && sums && dx && M > 0 && C > 0 && count > 0.f, "bn_bwd_apply: bad args");
-  SB_CHECK_ARG(!relu || y, "bn_bwd_apply: relu needs y");
+  SB_CHECK_ARG(!relu || y || scale_shift, "bn_bwd_apply: relu needs y or scale_shift");
   SB_CHECK_ARG(C % 8 == 0 && dy_pitch % 8 == 0 && x_pitch % 8 == 0 && dx_pitch % 8 == 0 &&
-                   (!relu || y_pitch % 8 == 0) && (!dres || dres_pitch % 8 == 0),
+                   (!(relu && y) || y_pitch % 8 == 0) && (!dres || dres_pitch % 8 == 0),
                "bn_bwd_apply: channels and pitches must be multiples of 8");
   const long long total = static_cast<long long>(M) * (C / 8);
   bn_bwd_apply_kernel<<<ew_grid_fixed_channels(total, 256, C / 8), 256, 0, stream>>>(
       static_cast<const bf16*>(dy), dy_pitch, static_cast<const bf16*>(y), y_pitch, static_cast<const bf16*>(x),
-      x_pitch, mean_invstd, gamma, sums, 1.f / count, M, C, relu, static_cast<bf16*>(dx), dx_pitch,
+      x_pitch, mean_invstd, gamma, scale_shift, sums, 1.f / count, M, C, relu, static_cast<bf16*>(dx), dx_pitch,
       static_cast<bf16*>(dres), dres_pitch, dgamma_dbeta);
   SB_LAUNCHED();
   return SEMSEG_OK;

@@ -82,43 +82,50 @@ ppm_pool_kernel(const __nv_bfloat16* __restrict__ x, int pitch, int N, int H, in
 }
 
 // dx[n,h,w,c] = sum over bins, over cells whose window contains (h,w): dpooled[n,cell,c] / window_size.
+// One warp per pixel: the (cell, 1/window) list of the pixel is derived once, then the lanes sweep the channels.
 __global__ void __launch_bounds__(256)
 ppm_pool_bwd_kernel(__nv_bfloat16* __restrict__ dx, int pitch, int N, int H, int W, int C, BinSet bs) {
+  const int lane = threadIdx.x & 31;
+  const long long npix = static_cast<long long>(N) * H * W;
   const int groups = C >> 3;
-  const long long total = static_cast<long long>(N) * H * W * groups;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long p = idx / groups;
-    const int c0 = static_cast<int>(idx - p * groups) << 3;
+  constexpr int kMaxCells = 4 * kMaxBins;  // up to 2x2 overlapping windows per bin
+  for (long long p = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); p < npix;
+       p += static_cast<long long>(gridDim.x) * (blockDim.x >> 5)) {
     const int wx = static_cast<int>(p % W);
     const int hh = static_cast<int>((p / W) % H);
     const int n = static_cast<int>(p / (static_cast<long long>(W) * H));
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const __nv_bfloat16* src[kMaxCells];
+    float inv[kMaxCells];
+    int cnt = 0;
     for (int k = 0; k < bs.nb; ++k) {
       const int b = bs.b[k];
-      const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(bs.ptr[k]);
-      // cells ci with hs <= hh < he: ci in [floor(hh*b/H) - 1, ...]; windows may overlap by one row when H % b != 0
-      int ci_lo = (hh * b) / H;
-      if (ci_lo > 0 && ((ci_lo * H + b - 1) / b) > hh) --ci_lo;
-      int cj_lo = (wx * b) / W;
-      if (cj_lo > 0 && ((cj_lo * W + b - 1) / b) > wx) --cj_lo;
-      for (int ci = ci_lo; ci < b; ++ci) {
+      const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(bs.ptr[k]) + static_cast<size_t>(n) * b * b * C;
+      for (int ci = (hh * b) / H; ci < b; ++ci) {
         const int hs = (ci * H) / b, he = ((ci + 1) * H + b - 1) / b;
         if (hs > hh) break;
         if (hh >= he) continue;
-        for (int cj = cj_lo; cj < b; ++cj) {
+        for (int cj = (wx * b) / W; cj < b; ++cj) {
           const int ws = (cj * W) / b, we = ((cj + 1) * W + b - 1) / b;
           if (ws > wx) break;
           if (wx >= we) continue;
-          const float inv = 1.f / static_cast<float>((he - hs) * (we - ws));
-          float f[8];
-          ld8(dp + (static_cast<size_t>(n) * b * b + ci * b + cj) * C + c0, f);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] = fmaf(f[q], inv, acc[q]);
+          if (cnt < kMaxCells) {
+            src[cnt] = dp + static_cast<size_t>(ci * b + cj) * C;
+            inv[cnt] = 1.f / static_cast<float>((he - hs) * (we - ws));
+            ++cnt;
+          }
         }
       }
     }
-    st8(dx + p * pitch + c0, acc);
+    for (int g = lane; g < groups; g += 32) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int i = 0; i < cnt; ++i) {
+        float f[8];
+        ld8(src[i] + g * 8, f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fmaf(f[q], inv[i], acc[q]);
+      }
+      st8(dx + p * pitch + g * 8, acc);
+    }
   }
 }
 
@@ -264,8 +271,8 @@ extern "C" int semseg_ppm_pool_bwd(void* const* dpooled, const int* bins, int nb
   BinSet bs;
   int r = make_binset(bins, dpooled, nb, &bs);
   if (r) return r;
-  const long long total = static_cast<long long>(N) * H * W * (C / 8);
-  ppm_pool_bwd_kernel<<<ew_blocks(total), 256, 0, stream>>>(static_cast<bf16*>(dx), dx_pitch, N, H, W, C, bs);
+  const long long warps = static_cast<long long>(N) * H * W;
+  ppm_pool_bwd_kernel<<<ew_blocks(warps * 32), 256, 0, stream>>>(static_cast<bf16*>(dx), dx_pitch, N, H, W, C, bs);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }

@@ -60,20 +60,19 @@ upsample_ce_fwd_kernel(const float* __restrict__ logits, int pitch, int N, int h
       const float* r1 = S + (i1 - i_base) * 6 * C;
       const size_t pix = (static_cast<size_t>(n) * Ho + y) * Wo + x;
       const long long t = target[pix];
-      float m = -INFINITY, vt = 0.f;
+      // online log-sum-exp: one interpolation per class; the running sum is rescaled when the maximum moves
+      float m = -INFINITY, vt = 0.f, s = 0.f;
       int am = 0;
       for (int c = 0; c < C; ++c) {
         const float v = l0h * (l0w * r0[cj0 + c] + l1w * r0[cj1 + c]) + l1h * (l0w * r1[cj0 + c] + l1w * r1[cj1 + c]);
         if (v > m) {
+          s = s * __expf(m - v) + 1.f;
           m = v;
           am = c;
+        } else {
+          s += __expf(v - m);
         }
         if (c == t) vt = v;
-      }
-      float s = 0.f;
-      for (int c = 0; c < C; ++c) {
-        const float v = l0h * (l0w * r0[cj0 + c] + l1w * r0[cj1 + c]) + l1h * (l0w * r1[cj0 + c] + l1w * r1[cj1 + c]);
-        s += __expf(v - m);
       }
       const float lse = m + __logf(s);
       if (argmax_out) argmax_out[pix] = am;

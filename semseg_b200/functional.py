@@ -64,18 +64,21 @@ def _finalize_stats(stats, bn, pg):
     return mi, ss, world
 
 
-def _bn_backward(ctx_pg, world, dy, y, raw, mi, gamma, relu, want_dres):
-    """Shared BN(+ReLU) backward: returns (d_raw, dres, dgamma, dbeta)."""
+def _bn_backward(ctx_pg, world, dy, y, raw, mi, gamma, relu, want_dres, ss=None):
+    """Shared BN(+ReLU) backward: returns (d_raw, dres, dgamma, dbeta). The ReLU mask comes from the saved output `y`,
+    or — when `y` is None and `ss` (scale/shift) is given, i.e. no residual — is recomputed from `raw` (saves one
+    tensor read in each of the two passes)."""
     n, h, w, c = raw.shape
     if not dy.is_contiguous():
         dy = dy.contiguous()
-    sums = ops.bn_bwd_reduce(dy, y if relu else None, raw, mi, relu)
+    sums = ops.bn_bwd_reduce(dy, y if relu else None, raw, mi, relu, scale_shift=ss if y is None else None)
     dbeta, dgamma = sums[0], sums[1]
     if ctx_pg is not None:
         dbeta, dgamma = dbeta.clone(), dgamma.clone()  # local sums feed dgamma/dbeta (DDP averages them)
         dist.all_reduce(sums, group=ctx_pg)
     count = float(n * h * w * world)
-    d_raw, dres, _ = ops.bn_bwd_apply(dy, y if relu else None, raw, mi, gamma, sums, count, relu, want_dres=want_dres)
+    d_raw, dres, _ = ops.bn_bwd_apply(dy, y if relu else None, raw, mi, gamma, sums, count, relu, want_dres=want_dres,
+                                      scale_shift=ss if y is None else None)
     return d_raw, dres, dgamma, dbeta
 
 
@@ -100,7 +103,9 @@ class _ConvBnAct(torch.autograd.Function):
         else:
             mi, ss, world = _finalize_stats(ops.bn_merge_partials(sp), bn, pg)
         y = ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)
-        ctx.save_for_backward(x, raw, y if relu else None, mi, gamma)
+        # ReLU mask for backward: with a residual it needs the saved output, otherwise it is recomputed from raw
+        need_y = relu and residual is not None
+        ctx.save_for_backward(x, raw, y if need_y else None, mi, gamma, ss if (relu and not need_y) else None)
         ctx.pw, ctx.k, ctx.dil, ctx.relu, ctx.pg, ctx.world = pw, k, dil, relu, pg, world
         ctx.has_res = residual is not None
         if out is not None:
@@ -109,10 +114,10 @@ class _ConvBnAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x, raw, y, mi, gamma = ctx.saved_tensors
+        x, raw, y, mi, gamma, ss = ctx.saved_tensors
         pw = ctx.pw
         d_raw, dres, dgamma, dbeta = _bn_backward(ctx.pg, ctx.world, dy, y, raw, mi, gamma, ctx.relu,
-                                                  ctx.has_res and ctx.needs_input_grad[4])
+                                                  ctx.has_res and ctx.needs_input_grad[4], ss)
         dx = None
         if ctx.needs_input_grad[0]:
             dx, _ = ops.conv_fprop(d_raw, pw.wd, pw.cin, ops.conv_taps(ctx.k, ctx.dil, transpose=True))
@@ -131,15 +136,16 @@ class _BnAct(torch.autograd.Function):
         pg = _sync_group(bn)
         mi, ss, world = _finalize_stats(stats, bn, pg)
         y = ops.bn_apply(raw, ss, residual=residual, relu=relu)
-        ctx.save_for_backward(raw, y if relu else None, mi, gamma)
+        need_y = relu and residual is not None
+        ctx.save_for_backward(raw, y if need_y else None, mi, gamma, ss if (relu and not need_y) else None)
         ctx.relu, ctx.pg, ctx.world, ctx.has_res = relu, pg, world, residual is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        raw, y, mi, gamma = ctx.saved_tensors
+        raw, y, mi, gamma, ss = ctx.saved_tensors
         d_raw, dres, dgamma, dbeta = _bn_backward(ctx.pg, ctx.world, dy, y, raw, mi, gamma, ctx.relu,
-                                                  ctx.has_res and ctx.needs_input_grad[3])
+                                                  ctx.has_res and ctx.needs_input_grad[3], ss)
         return d_raw, dgamma, dbeta, dres, None, None
 
 

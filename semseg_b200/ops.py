@@ -312,7 +312,7 @@ def bn_apply(x, scale_shift, residual=None, relu=True, out=None):
     return out
 
 
-def bn_bwd_reduce(dy, y, x, mean_invstd, relu):
+def bn_bwd_reduce(dy, y, x, mean_invstd, relu, scale_shift=None):
     lib = _lib.load()
     n, h, w, c, dp = _nhwc_meta(dy)
     _, _, _, _, xp = _nhwc_meta(x)
@@ -320,13 +320,13 @@ def bn_bwd_reduce(dy, y, x, mean_invstd, relu):
     m = n * h * w
     ws, nf = bn_workspace(m, c, dy.device)
     sums = torch.empty((2, c), dtype=torch.float32, device=dy.device)
-    _lib.check(lib.semseg_bn_bwd_reduce(_ptr(dy), dp, _ptr(y), yp, _ptr(x), xp, _ptr(mean_invstd), m, c,
-                                        int(bool(relu)), _ptr(ws), nf, _ptr(sums), _stream()),
+    _lib.check(lib.semseg_bn_bwd_reduce(_ptr(dy), dp, _ptr(y), yp, _ptr(x), xp, _ptr(mean_invstd), _ptr(scale_shift),
+                                        m, c, int(bool(relu)), _ptr(ws), nf, _ptr(sums), _stream()),
                "semseg_bn_bwd_reduce")
     return sums
 
 
-def bn_bwd_apply(dy, y, x, mean_invstd, gamma, sums, count, relu, want_dres=False):
+def bn_bwd_apply(dy, y, x, mean_invstd, gamma, sums, count, relu, want_dres=False, scale_shift=None):
     """Returns (dx bf16, dres bf16 or None, dgamma_dbeta [2][C])."""
     lib = _lib.load()
     n, h, w, c, dp = _nhwc_meta(dy)
@@ -336,7 +336,7 @@ def bn_bwd_apply(dy, y, x, mean_invstd, gamma, sums, count, relu, want_dres=Fals
     dres = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device) if want_dres else None
     dgb = torch.empty((2, c), dtype=torch.float32, device=dy.device)
     _lib.check(lib.semseg_bn_bwd_apply(_ptr(dy), dp, _ptr(y), yp, _ptr(x), xp, _ptr(mean_invstd), _ptr(gamma),
-                                       _ptr(sums), float(count), n * h * w, c, int(bool(relu)), _ptr(dx), c,
+                                       _ptr(scale_shift), _ptr(sums), float(count), n * h * w, c, int(bool(relu)), _ptr(dx), c,
                                        _ptr(dres), c, _ptr(dgb), _stream()), "semseg_bn_bwd_apply")
     return dx, dres, dgb
 
