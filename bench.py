@@ -317,7 +317,8 @@ def run_b200_arm(args):
                                                   args.size, args.size, args.classes, args.batch),
                    "global_batch": args.batch * world, "parallelism": "dp%d" % world,
                    "l2": "inputs larger than L2: each step streams > 10 GB of activations through the 126 MB L2",
-                   "optimizer": "SGD momentum 0.9 wd 1e-4, 8 param groups", "sync_bn": world > 1},
+                   "optimizer": "SGD momentum 0.9 wd 1e-4, 8 param groups", "sync_bn": world > 1,
+                   "syncbn_exchange": __import__("semseg_b200.p2p", fromlist=["x"]).exchange_kind()},
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),

@@ -165,6 +165,21 @@ int semseg_bn_finalize(const float* rank_stats, int R, int C, const float* gamma
 int semseg_bn_finalize_partials(const float* stats_partial, int rows, int C, const float* gamma, const float* beta, float eps, float momentum,
                                 float* running_mean, float* running_var, float* mean_invstd, float* scale_shift,
                                 void* stream);
+/* SyncBatchNorm exchange over NVLink peer memory instead of NCCL (one kernel per exchange). peer_bufs[world] /
+ * peer_flags[world] are device pointers into every rank's symmetric (peer-mapped) allocation: a float buffer of
+ * n_slots*slot_floats and a zero-initialised uint32 flag array [n_slots][world]; `counter` is a zeroed local uint32;
+ * `slot` must be unique per exchange within a step and `seq` strictly increasing per step (same on every rank).
+ *   finalize_p2p   : per-CTA conv partials -> exchange (mean, M2, n) -> cross-rank merge in rank order -> finalise.
+ *   bwd_reduce_p2p : local [sum dz, sum dz*xhat] -> sums_local; exchanged and added in rank order -> sums_total. */
+int semseg_bn_finalize_p2p(const float* stats_partial, int rows, int C, const float* gamma, const float* beta,
+                           float eps, float momentum, float* running_mean, float* running_var, float* mean_invstd,
+                           float* scale_shift, void* const* peer_bufs, void* const* peer_flags, void* counter,
+                           int world, int rank, int slot, int slot_floats, unsigned seq, void* stream);
+int semseg_bn_bwd_reduce_p2p(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x, int x_pitch,
+                             const float* mean_invstd, const float* scale_shift, int M, int C, int relu,
+                             float* workspace, long long workspace_floats, float* sums_local, float* sums_total,
+                             void* const* peer_bufs, void* const* peer_flags, void* counter, int world, int rank,
+                             int slot, int slot_floats, unsigned seq, void* stream);
 /* Eval-mode folding: scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
 int semseg_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, int C, float* scale_shift, void* stream);

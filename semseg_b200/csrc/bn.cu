@@ -564,6 +564,139 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, int a_pitch
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SyncBatchNorm statistics exchange over NVLink peer memory (torch symmetric memory): every rank publishes its
+// per-channel block in its own peer-mapped buffer, raises a flag in every peer's flag array, waits for the peers'
+// flags and then reads their blocks directly over NVLink. One kernel per exchange, no NCCL call, no stream hop;
+// the cross-rank merge is done in rank order on every rank, so all ranks compute bit-identical statistics.
+struct PeerArgs {
+  float* buf[8];        // peer-mapped data buffers (buf[rank] is local)
+  unsigned* flags[8];   // peer-mapped flag arrays [slots][world]
+  unsigned* counter;    // local block-arrival counter (self-resetting)
+  int world, rank, slot, slot_floats;
+  unsigned seq;         // strictly increasing per training step
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by every thread of every block after the block's own data has been stored to buf[rank].
+__device__ __forceinline__ void peer_publish_and_wait(const PeerArgs& pa) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned prev = atomicAdd(pa.counter, 1u);
+    if (prev == gridDim.x - 1) {  // last block of this rank: everything is published
+      *pa.counter = 0u;
+      __threadfence_system();
+      for (int p = 0; p < pa.world; ++p) st_release_sys(pa.flags[p] + pa.slot * pa.world + pa.rank, pa.seq);
+    }
+  }
+  if (threadIdx.x < pa.world) {
+    const unsigned* f = pa.flags[pa.rank] + pa.slot * pa.world + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) != pa.seq) {
+      if (clock64() - t0 > 8000000000LL) {  // a missing peer must not hang the GPU
+        printf("semseg_b200: SyncBN peer exchange timed out (rank %d waiting for rank %d, slot %d)\n", pa.rank,
+               static_cast<int>(threadIdx.x), pa.slot);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Forward: merge this rank's conv partials, exchange (mean, M2, n), merge over ranks, finalise.
+__global__ void bn_finalize_p2p_kernel(const float* __restrict__ part, int T, int C, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, float momentum,
+                                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                                       float* __restrict__ mean_invstd, float* __restrict__ scale_shift, PeerArgs pa) {
+  __shared__ Moments sm[32][33];
+  const int cl = threadIdx.x & 31;
+  const int tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  Moments acc = {0.f, 0.f, 0.f};
+  if (c < C)
+    for (int t = tl; t < T; t += 32) acc = merge(acc, conv_row_moments(part, t, C, c));
+  sm[tl][cl] = acc;
+  __syncthreads();
+  const size_t off = static_cast<size_t>(pa.slot) * pa.slot_floats;
+  if (tl == 0 && c < C) {
+    Moments r = sm[0][cl];
+    for (int i = 1; i < 32; ++i) r = merge(r, sm[i][cl]);
+    float* own = pa.buf[pa.rank] + off;
+    own[c] = r.mean;
+    own[C + c] = r.m2;
+    own[2 * C + c] = r.n;
+  }
+  peer_publish_and_wait(pa);
+  if (tl == 0 && c < C) {
+    Moments r = {0.f, 0.f, 0.f};
+    for (int p = 0; p < pa.world; ++p) {
+      const float* b = pa.buf[p] + off;
+      Moments m;
+      m.mean = ld_relaxed_sys(b + c);
+      m.m2 = ld_relaxed_sys(b + C + c);
+      m.n = ld_relaxed_sys(b + 2 * C + c);
+      r = merge(r, m);
+    }
+    const float var = r.n > 0.f ? r.m2 / r.n : 0.f;
+    const float invstd = rsqrtf(var + eps);
+    mean_invstd[c] = r.mean;
+    mean_invstd[C + c] = invstd;
+    const float sc = (gamma ? gamma[c] : 1.f) * invstd;
+    scale_shift[c] = sc;
+    scale_shift[C + c] = (beta ? beta[c] : 0.f) - r.mean * sc;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * r.mean;
+    if (running_var) {
+      const float unb = r.n > 1.f ? r.m2 / (r.n - 1.f) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+    }
+  }
+}
+
+// Backward: finish the local chunk reduction, exchange [sum dz, sum dz*xhat], add over ranks in rank order.
+//   sums_local [2][C] (feeds dgamma/dbeta, averaged later by DDP), sums_total [2][C] (feeds dx).
+__global__ void bn_bwd_reduce_final_p2p_kernel(const float* __restrict__ part, int chunks, int C,
+                                               float* __restrict__ sums_local, float* __restrict__ sums_total,
+                                               PeerArgs pa) {
+  __shared__ float sm[32][33];
+  const int cl = threadIdx.x & 31;
+  const int tl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + cl;  // over 2*C
+  float acc = 0.f;
+  if (idx < 2 * C) {
+    const int which = idx / C, c = idx - which * C;
+    for (int t = tl; t < chunks; t += 32) acc += part[(static_cast<size_t>(t) * 2 + which) * C + c];
+  }
+  sm[tl][cl] = acc;
+  __syncthreads();
+  const size_t off = static_cast<size_t>(pa.slot) * pa.slot_floats;
+  if (tl == 0 && idx < 2 * C) {
+    float r = 0.f;
+    for (int i = 0; i < 32; ++i) r += sm[i][cl];
+    sums_local[idx] = r;
+    pa.buf[pa.rank][off + idx] = r;
+  }
+  peer_publish_and_wait(pa);
+  if (tl == 0 && idx < 2 * C) {
+    float r = 0.f;
+    for (int p = 0; p < pa.world; ++p) r += ld_relaxed_sys(pa.buf[p] + off + idx);
+    sums_total[idx] = r;
+  }
+}
+
 static int ew_grid(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -740,6 +873,72 @@ extern "C" int semseg_add_bf16(const void* a, int a_pitch, const void* b, int b_
   add_bf16_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(a), a_pitch,
                                                            static_cast<const bf16*>(b), b_pitch,
                                                            static_cast<bf16*>(out), out_pitch, M, C);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+
+static int fill_peer_args(sb::PeerArgs* pa, void* const* peer_bufs, void* const* peer_flags, void* counter, int world,
+                          int rank, int slot, int slot_floats, unsigned seq, int need_floats) {
+  SB_CHECK_ARG(peer_bufs && peer_flags && counter, "p2p: null peer tables");
+  SB_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "p2p: world %d rank %d unsupported", world, rank);
+  SB_CHECK_ARG(slot >= 0 && need_floats <= slot_floats, "p2p: slot too small (%d > %d floats)", need_floats,
+               slot_floats);
+  for (int i = 0; i < world; ++i) {
+    SB_CHECK_ARG(peer_bufs[i] && peer_flags[i], "p2p: null peer pointer %d", i);
+    pa->buf[i] = static_cast<float*>(peer_bufs[i]);
+    pa->flags[i] = static_cast<unsigned*>(peer_flags[i]);
+  }
+  pa->counter = static_cast<unsigned*>(counter);
+  pa->world = world;
+  pa->rank = rank;
+  pa->slot = slot;
+  pa->slot_floats = slot_floats;
+  pa->seq = seq;
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_bn_finalize_p2p(const float* stats_partial, int rows, int C, const float* gamma,
+                                      const float* beta, float eps, float momentum, float* running_mean,
+                                      float* running_var, float* mean_invstd, float* scale_shift,
+                                      void* const* peer_bufs, void* const* peer_flags, void* counter, int world,
+                                      int rank, int slot, int slot_floats, unsigned seq, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(stats_partial && mean_invstd && scale_shift && rows > 0 && C > 0, "bn_finalize_p2p: bad args");
+  sb::PeerArgs pa;
+  int r = fill_peer_args(&pa, peer_bufs, peer_flags, counter, world, rank, slot, slot_floats, seq, 3 * C);
+  if (r) return r;
+  bn_finalize_p2p_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, rows, C, gamma, beta, eps, momentum,
+                                                          running_mean, running_var, mean_invstd, scale_shift, pa);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_bn_bwd_reduce_p2p(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x,
+                                        int x_pitch, const float* mean_invstd, const float* scale_shift, int M, int C,
+                                        int relu, float* workspace, long long workspace_floats, float* sums_local,
+                                        float* sums_total, void* const* peer_bufs, void* const* peer_flags,
+                                        void* counter, int world, int rank, int slot, int slot_floats, unsigned seq,
+                                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(dy && x && mean_invstd && workspace && sums_local && sums_total && M > 0 && C > 0,
+               "bn_bwd_reduce_p2p: bad args");
+  SB_CHECK_ARG(!relu || y || scale_shift, "bn_bwd_reduce_p2p: relu needs y or scale_shift");
+  SB_CHECK_ARG(C % 8 == 0 && dy_pitch % 8 == 0 && x_pitch % 8 == 0 && (!(relu && y) || y_pitch % 8 == 0),
+               "bn_bwd_reduce_p2p: channels and pitches must be multiples of 8");
+  SB_CHECK_ARG(workspace_floats >= semseg_bn_workspace_floats(M, C), "bn_bwd_reduce_p2p: workspace too small");
+  sb::PeerArgs pa;
+  int r = fill_peer_args(&pa, peer_bufs, peer_flags, counter, world, rank, slot, slot_floats, seq, 2 * C);
+  if (r) return r;
+  const int rows = chunk_rows(M);
+  const int chunks = cdiv(M, rows);
+  dim3 grid(cdiv(C, 64), chunks);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_pitch, static_cast<const bf16*>(y),
+                                                 y_pitch, static_cast<const bf16*>(x), x_pitch, mean_invstd,
+                                                 scale_shift, M, C, relu, rows, workspace);
+  SB_LAUNCHED();
+  bn_bwd_reduce_final_p2p_kernel<<<cdiv(2 * C, 32), 1024, 0, stream>>>(workspace, chunks, C, sums_local, sums_total,
+                                                                      pa);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }

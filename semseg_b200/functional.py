@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from . import p2p
 from .dist_utils import gather_rank_stats
 from .ops import EPI_RAW, EPI_AFFINE, EPI_F32
 
@@ -71,11 +72,17 @@ def _bn_backward(ctx_pg, world, dy, y, raw, mi, gamma, relu, want_dres, ss=None)
     n, h, w, c = raw.shape
     if not dy.is_contiguous():
         dy = dy.contiguous()
-    sums = ops.bn_bwd_reduce(dy, y if relu else None, raw, mi, relu, scale_shift=ss if y is None else None)
-    dbeta, dgamma = sums[0], sums[1]
-    if ctx_pg is not None:
-        dbeta, dgamma = dbeta.clone(), dgamma.clone()  # local sums feed dgamma/dbeta (DDP averages them)
-        dist.all_reduce(sums, group=ctx_pg)
+    px = p2p.get_exchange(ctx_pg) if ctx_pg is not None else None
+    if px is not None and 2 * c <= p2p.SLOT_FLOATS:
+        # cross-rank sum over NVLink peer memory inside the reduction kernel (no NCCL call)
+        local, sums = ops.bn_bwd_reduce_p2p(dy, y if relu else None, raw, mi, relu, ss if y is None else None, px)
+        dbeta, dgamma = local[0], local[1]
+    else:
+        sums = ops.bn_bwd_reduce(dy, y if relu else None, raw, mi, relu, scale_shift=ss if y is None else None)
+        dbeta, dgamma = sums[0], sums[1]
+        if ctx_pg is not None:
+            dbeta, dgamma = dbeta.clone(), dgamma.clone()  # local sums feed dgamma/dbeta (DDP averages them)
+            dist.all_reduce(sums, group=ctx_pg)
     count = float(n * h * w * world)
     d_raw, dres, _ = ops.bn_bwd_apply(dy, y if relu else None, raw, mi, gamma, sums, count, relu, want_dres=want_dres,
                                       scale_shift=ss if y is None else None)
@@ -101,7 +108,18 @@ class _ConvBnAct(torch.autograd.Function):
                 bn.num_batches_tracked.add_(1)
             world = 1
         else:
-            mi, ss, world = _finalize_stats(ops.bn_merge_partials(sp), bn, pg)
+            px = p2p.get_exchange(pg)
+            if px is not None and 3 * pw.cout <= p2p.SLOT_FLOATS:
+                # statistics exchanged over NVLink peer memory inside the finalise kernel (no NCCL call)
+                track = bn.track_running_stats and bn.running_mean is not None
+                mi, ss = ops.bn_finalize_p2p(sp, bn.weight, bn.bias, bn.eps, _bn_momentum(bn) if track else 0.0,
+                                             bn.running_mean if track else None,
+                                             bn.running_var if track else None, px)
+                if track and bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked.add_(1)
+                world = px.world
+            else:
+                mi, ss, world = _finalize_stats(ops.bn_merge_partials(sp), bn, pg)
         y = ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)
         # ReLU mask for backward: with a residual it needs the saved output, otherwise it is recomputed from raw
         need_y = relu and residual is not None

@@ -468,3 +468,38 @@ def maxpool3x3s2_bwd(x, dy):
     _lib.check(lib.semseg_maxpool3x3s2_bwd(_ptr(x), _ptr(dy), _ptr(dx), n, h, w, c, _stream()),
                "semseg_maxpool3x3s2_bwd")
     return dx
+
+
+# ------------------------------------------------------------------------------------------------ SyncBN over NVLink
+def bn_finalize_p2p(stats_partial, gamma, beta, eps, momentum, running_mean, running_var, px):
+    """Like bn_finalize_partials, with the cross-rank exchange done inside the kernel over peer memory (px)."""
+    lib = _lib.load()
+    t, _, c = stats_partial.shape
+    buf = torch.empty((4, c), dtype=torch.float32, device=stats_partial.device)
+    mi, ss = buf[:2], buf[2:]
+    slot, seq = px.next()
+    _lib.check(lib.semseg_bn_finalize_p2p(_ptr(stats_partial), t, c, _ptr(gamma), _ptr(beta), float(eps),
+                                          float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(mi), _ptr(ss),
+                                          px.data_ptrs, px.flag_ptrs, _ptr(px.counter), px.world, px.rank, slot,
+                                          int(__import__("semseg_b200.p2p", fromlist=["x"]).SLOT_FLOATS), seq,
+                                          _stream()), "semseg_bn_finalize_p2p")
+    return mi, ss
+
+
+def bn_bwd_reduce_p2p(dy, y, x, mean_invstd, relu, scale_shift, px):
+    """-> (sums_local [2][C], sums_total [2][C]) with the all-reduce done over peer memory."""
+    lib = _lib.load()
+    n, h, w, c, dp = _nhwc_meta(dy)
+    _, _, _, _, xp = _nhwc_meta(x)
+    yp = _nhwc_meta(y)[4] if y is not None else 0
+    m = n * h * w
+    ws, nf = bn_workspace(m, c, dy.device)
+    out = torch.empty((2, 2, c), dtype=torch.float32, device=dy.device)
+    slot, seq = px.next()
+    _lib.check(lib.semseg_bn_bwd_reduce_p2p(_ptr(dy), dp, _ptr(y), yp, _ptr(x), xp, _ptr(mean_invstd),
+                                            _ptr(scale_shift), m, c, int(bool(relu)), _ptr(ws), nf, _ptr(out[0]),
+                                            _ptr(out[1]), px.data_ptrs, px.flag_ptrs, _ptr(px.counter), px.world,
+                                            px.rank, slot,
+                                            int(__import__("semseg_b200.p2p", fromlist=["x"]).SLOT_FLOATS), seq,
+                                            _stream()), "semseg_bn_bwd_reduce_p2p")
+    return out[0], out[1]

@@ -1,0 +1,70 @@
+"""SyncBatchNorm statistics exchange over NVLink peer memory (torch symmetric memory).
+
+One process per GPU; every rank allocates the same symmetric buffer, `rendezvous` maps all peers' buffers into this
+process, and the exchange kernels (csrc/bn.cu: bn_finalize_p2p, bn_bwd_reduce_p2p) publish / flag / read directly over
+NVLink — one kernel per BatchNorm exchange instead of merge-kernel + NCCL collective + finalise-kernel.
+If symmetric memory cannot be set up (no P2P access, single process, SEMSEG_B200_SYNCBN=nccl) the callers use the
+NCCL path (torch.distributed all_gather / all_reduce); both paths compute the same statistics.
+"""
+import ctypes
+import os
+
+import torch
+import torch.distributed as dist
+
+N_SLOTS = 512
+SLOT_FLOATS = 3 * 4096          # (mean, M2, n) for up to 4096 channels
+
+_exchanges = {}
+
+
+class PeerExchange:
+    def __init__(self, pg):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world = dist.get_world_size(pg)
+        self.rank = dist.get_rank(pg)
+        if self.world > 8:
+            raise RuntimeError("peer exchange supports up to 8 ranks (one NVSwitch domain)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        flag_words = N_SLOTS * self.world
+        self.buf = symm_mem.empty(flag_words + N_SLOTS * SLOT_FLOATS, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, pg)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.flag_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.data_ptrs = (ctypes.c_void_p * self.world)(*[p + 4 * flag_words for p in ptrs])
+        self.counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        self.handle.barrier()           # every rank's flags are zero before the first exchange
+        torch.cuda.synchronize()
+        self.calls = 0
+
+    def next(self):
+        """(slot, seq) of the next exchange: identical on every rank because all ranks run the same op sequence."""
+        k = self.calls
+        self.calls += 1
+        return k % N_SLOTS, k // N_SLOTS + 1
+
+
+def get_exchange(pg):
+    """PeerExchange for a process group, or None when the NCCL path must be used."""
+    if os.environ.get("SEMSEG_B200_SYNCBN", "p2p").lower() == "nccl":
+        return None
+    key = id(pg)
+    if key not in _exchanges:
+        try:
+            _exchanges[key] = PeerExchange(pg)
+        except Exception as e:      # noqa: BLE001 - symmetric memory unsupported here: use NCCL
+            if dist.get_rank(pg) == 0:
+                print("semseg_b200: NVLink peer exchange unavailable (%s); SyncBN statistics go through NCCL" %
+                      str(e).splitlines()[0][:160])
+            _exchanges[key] = None
+    return _exchanges[key]
+
+
+def exchange_kind(pg=None):
+    if not (dist.is_available() and dist.is_initialized()):
+        return "none"
+    pg = pg if pg is not None else dist.group.WORLD
+    ex = _exchanges.get(id(pg))
+    return "nvlink-p2p" if ex is not None else "nccl"
