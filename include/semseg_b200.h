@@ -144,6 +144,12 @@ int semseg_nhwc_bf16_to_nchw_f32(const void* in, float* out, int N, int C, int H
 int semseg_nhwc_f32_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W, int in_pitch,
                                 void* stream);
 
+/* 2x2 phase decomposition used to run stride-2 convolutions (model/resnet.py:108 conv1, layer2.0 conv2 and
+ * downsample) on the stride-1 tensor-core kernel:
+ *   xp [4][N][Hh][Wh][C], Hh = (H+1)/2:  xp[ph*2+pw][n][i][j] = x[n][2i+ph][2j+pw] (zero outside x). */
+int semseg_space_to_phases(const void* x, int x_pitch, int N, int H, int W, int C, void* xp, void* stream);
+int semseg_phases_to_space(const void* xp, int N, int H, int W, int C, void* x, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm (training statistics, apply, backward) on NHWC bf16 tensors, fp32 statistics.
  */

@@ -77,10 +77,81 @@ __global__ void pack_wd_kernel(const float* __restrict__ w, int Cout, int Cin, i
   }
 }
 
+// Stride-2 convolutions run on the stride-1 tensor-core kernel through a 2x2 phase decomposition:
+//   xp[(ph*2+pw)*N + n][i][j][c] = x[n][2i+ph][2j+pw][c]   (zero where 2i+ph >= H or 2j+pw >= W)
+// so tap (r, s) of a stride-2 conv reads phase ((r+1)&1, (s+1)&1) at a shift of -1 or 0.
+__global__ void space_to_phases_kernel(const __nv_bfloat16* __restrict__ x, int pitch, int N, int H, int W, int C,
+                                       __nv_bfloat16* __restrict__ xp, int Hh, int Wh) {
+  const int groups = C >> 3;
+  const long long total = 4LL * N * Hh * Wh * groups;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    long long p = idx / groups;
+    const int j = static_cast<int>(p % Wh);
+    p /= Wh;
+    const int i = static_cast<int>(p % Hh);
+    p /= Hh;
+    const int n = static_cast<int>(p % N);
+    const int q = static_cast<int>(p / N);
+    const int h = 2 * i + (q >> 1), w = 2 * j + (q & 1);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (h < H && w < W)
+      v = *reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + h) * W + w) * pitch + g * 8);
+    *reinterpret_cast<uint4*>(xp + (idx / groups) * C + g * 8) = v;
+  }
+}
+
+__global__ void phases_to_space_kernel(const __nv_bfloat16* __restrict__ xp, int N, int H, int W, int C, int Hh,
+                                       int Wh, __nv_bfloat16* __restrict__ x) {
+  const int groups = C >> 3;
+  const long long total = static_cast<long long>(N) * H * W * groups;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    long long p = idx / groups;
+    const int w = static_cast<int>(p % W);
+    p /= W;
+    const int h = static_cast<int>(p % H);
+    const int n = static_cast<int>(p / H);
+    const int q = (h & 1) * 2 + (w & 1);
+    const size_t src = (((static_cast<size_t>(q) * N + n) * Hh + (h >> 1)) * Wh + (w >> 1)) * C + g * 8;
+    *reinterpret_cast<uint4*>(x + (idx / groups) * C + g * 8) = *reinterpret_cast<const uint4*>(xp + src);
+  }
+}
+
 }  // namespace sb
 
 using namespace sb;
 typedef __nv_bfloat16 bf16;
+
+extern "C" int semseg_space_to_phases(const void* x, int x_pitch, int N, int H, int W, int C, void* xp,
+                                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(x && xp && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && x_pitch % 8 == 0,
+               "space_to_phases: bad args");
+  const int Hh = (H + 1) / 2, Wh = (W + 1) / 2;
+  const long long total = 4LL * N * Hh * Wh * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  space_to_phases_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(x), x_pitch, N, H,
+                                                                           W, C, static_cast<bf16*>(xp), Hh, Wh);
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_phases_to_space(const void* xp, int N, int H, int W, int C, void* x, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(x && xp && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "phases_to_space: bad args");
+  const int Hh = (H + 1) / 2, Wh = (W + 1) / 2;
+  const long long total = static_cast<long long>(N) * H * W * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  phases_to_space_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(xp), N, H, W, C,
+                                                                           Hh, Wh, static_cast<bf16*>(x));
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
 
 extern "C" int semseg_pack_weights(const float* w_oihw, int Cout, int Cin, int taps, void* wf, int rows_f, int cols_f,
                                    void* wd, int rows_d, int cols_d, void* stream_) {

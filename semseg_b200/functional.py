@@ -91,16 +91,29 @@ def _bn_backward(ctx_pg, world, dy, y, raw, mi, gamma, relu, want_dres, ss=None)
 
 # ------------------------------------------------------------------------------------------------ conv+bn+act
 class _ConvBnAct(torch.autograd.Function):
-    """Stride-1 conv (1x1 / 3x3, any dilation) + training BatchNorm + optional residual + optional ReLU."""
+    """conv (1x1 / 3x3; stride 1 with any dilation, or stride 2) + training BatchNorm + optional residual + ReLU.
+
+    Stride-2 convs (stem conv1, layer2.0 conv2 / downsample — model/resnet.py:108,130-137) run on the same
+    stride-1 tensor-core kernel through a 2x2 phase decomposition of the input (ops.space_to_phases): tap (r, s)
+    reads phase ((r+1)&1, (s+1)&1) shifted by -1 or 0; dgrad is one small conv per phase, wgrad reads the phases."""
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, conv, bn, relu, out):
         pw = packed(conv)
-        k, dil = conv.kernel_size[0], conv.dilation[0]
-        raw, sp = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(k, dil), stats=True)
+        k, dil, stride = conv.kernel_size[0], conv.dilation[0], conv.stride[0]
+        n, h, w, cx = x.shape
+        if stride == 1:
+            xin, img_add, out_nhw = x, None, None
+            taps = ops.conv_taps(k, dil)
+        else:
+            xin = ops.space_to_phases(x)                     # [4N, Hh, Wh, C]
+            t2 = ops.conv_taps_s2(k, n)
+            taps, img_add = [t[:3] for t in t2], [t[3] for t in t2]
+            out_nhw = (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1)
+        raw, sp = ops.conv_fprop(xin, pw.wf, pw.cout, taps, stats=True, img_add=img_add, out_nhw=out_nhw)
         pg = _sync_group(bn)
         if pg is None:
-            # single rank: merge the per-tile partials and finalise in one launch
+            # single rank: merge the per-CTA partials and finalise in one launch
             track = bn.track_running_stats and bn.running_mean is not None
             mi, ss = ops.bn_finalize_partials(sp, bn.weight, bn.bias, bn.eps, _bn_momentum(bn) if track else 0.0,
                                               bn.running_mean if track else None, bn.running_var if track else None)
@@ -123,8 +136,9 @@ class _ConvBnAct(torch.autograd.Function):
         y = ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)
         # ReLU mask for backward: with a residual it needs the saved output, otherwise it is recomputed from raw
         need_y = relu and residual is not None
-        ctx.save_for_backward(x, raw, y if need_y else None, mi, gamma, ss if (relu and not need_y) else None)
-        ctx.pw, ctx.k, ctx.dil, ctx.relu, ctx.pg, ctx.world = pw, k, dil, relu, pg, world
+        ctx.save_for_backward(xin, raw, y if need_y else None, mi, gamma, ss if (relu and not need_y) else None)
+        ctx.pw, ctx.k, ctx.dil, ctx.stride, ctx.relu, ctx.pg, ctx.world = pw, k, dil, stride, relu, pg, world
+        ctx.in_shape = (n, h, w, cx)
         ctx.has_res = residual is not None
         if out is not None:
             ctx.mark_dirty(out)
@@ -132,16 +146,35 @@ class _ConvBnAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x, raw, y, mi, gamma, ss = ctx.saved_tensors
+        xin, raw, y, mi, gamma, ss = ctx.saved_tensors
         pw = ctx.pw
+        n, h, w, cx = ctx.in_shape
         d_raw, dres, dgamma, dbeta = _bn_backward(ctx.pg, ctx.world, dy, y, raw, mi, gamma, ctx.relu,
                                                   ctx.has_res and ctx.needs_input_grad[4], ss)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx, _ = ops.conv_fprop(d_raw, pw.wd, pw.cin, ops.conv_taps(ctx.k, ctx.dil, transpose=True))
-        dw = None
-        if ctx.needs_input_grad[1]:
-            dw = ops.conv_wgrad(x, d_raw, pw.cin, pw.cout, ops.conv_taps(ctx.k, ctx.dil))
+        dx = dw = None
+        if ctx.stride == 1:
+            if ctx.needs_input_grad[0]:
+                dx, _ = ops.conv_fprop(d_raw, pw.wd, pw.cin, ops.conv_taps(ctx.k, ctx.dil, transpose=True))
+            if ctx.needs_input_grad[1]:
+                dw = ops.conv_wgrad(xin, d_raw, cx, pw.cout, ops.conv_taps(ctx.k, ctx.dil))
+        else:
+            t2 = ops.conv_taps_s2(ctx.k, n)
+            if ctx.needs_input_grad[0]:
+                if pw.cin % 64 != 0:
+                    raise NotImplementedError("semseg_b200: input gradient of a stride-2 conv needs Cin % 64 == 0")
+                hh, wh = xin.shape[1], xin.shape[2]
+                dxp = torch.empty((4 * n, hh, wh, pw.cin), dtype=torch.bfloat16, device=dy.device)
+                for q in range(4):
+                    sub = [(-t[0], -t[1], t[2]) for t in t2 if t[4] == (q >> 1, q & 1)]
+                    if sub:      # dx of phase q: conv of d_raw with the taps that read this phase (mirrored shifts)
+                        ops.conv_fprop(d_raw, pw.wd, pw.cin, sub, out=dxp[q * n:(q + 1) * n], out_nhw=(n, hh, wh))
+                    else:
+                        dxp[q * n:(q + 1) * n].zero_()
+                dx = ops.phases_to_space(dxp, n, h, w)
+            if ctx.needs_input_grad[1]:
+                dw = ops.conv_wgrad(xin, d_raw, cx, pw.cout, [t[:2] for t in t2], img_add=[t[3] for t in t2])
+        if dw is not None and cx != pw.cin:
+            dw = dw[:, :pw.cin].contiguous()          # input channels were zero-padded to a multiple of 8 (stem)
         return dx, dw, dgamma, dbeta, dres, None, None, None, None
 
 
@@ -168,15 +201,18 @@ class _BnAct(torch.autograd.Function):
 
 
 def _is_native_conv(conv, cin):
-    return (conv.kernel_size in ((1, 1), (3, 3)) and conv.stride == (1, 1) and conv.groups == 1 and
-            conv.padding == (conv.dilation[0] * (conv.kernel_size[0] // 2),) * 2 and
-            conv.dilation[0] == conv.dilation[1] and cin % 8 == 0 and conv.out_channels % 64 == 0 and
-            conv.bias is None)
+    """Convs the tensor-core kernel covers: 1x1 / 3x3 'same' convs, stride 1 (any dilation) or stride 2 (dilation 1)."""
+    ok = (conv.kernel_size in ((1, 1), (3, 3)) and conv.groups == 1 and conv.bias is None and
+          conv.padding == (conv.dilation[0] * (conv.kernel_size[0] // 2),) * 2 and
+          conv.dilation[0] == conv.dilation[1] and cin % 8 == 0 and conv.out_channels % 64 == 0)
+    if conv.stride == (1, 1):
+        return ok
+    return ok and conv.stride == (2, 2) and conv.dilation == (1, 1)
 
 
 def _library_conv(x, conv):
-    """cuDNN channels-last bf16 path for the three convs the tensor-core kernel does not cover yet
-    (3-channel stem conv and the two stride-2 convs of layer2.0: 0.7 % of the network's FLOPs)."""
+    """cuDNN channels-last bf16 path for convolutions outside the kernel's coverage (none in PSPNet / PSANet: every
+    conv of the reference networks, including the stride-2 ones, runs on the tensor-core kernel)."""
     xn = x.permute(0, 3, 1, 2)  # NCHW view of the NHWC buffer (= channels_last)
     if xn.shape[1] != conv.in_channels:
         xn = xn[:, :conv.in_channels]
@@ -195,8 +231,15 @@ def conv_bn_act(x, conv, bn, relu=True, residual=None, out=None):
                                       "run eval under torch.no_grad()")
         if native:
             pw = packed(conv, need_dgrad=False)
-            y, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(conv.kernel_size[0], conv.dilation[0]),
-                                     epi=EPI_AFFINE, relu=relu, scale=ss[0], shift=ss[1], residual=residual, out=out)
+            if conv.stride == (1, 1):
+                y, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(conv.kernel_size[0], conv.dilation[0]),
+                                      epi=EPI_AFFINE, relu=relu, scale=ss[0], shift=ss[1], residual=residual, out=out)
+            else:
+                n, h, w, _ = x.shape
+                t2 = ops.conv_taps_s2(conv.kernel_size[0], n)
+                y, _ = ops.conv_fprop(ops.space_to_phases(x), pw.wf, pw.cout, [t[:3] for t in t2], epi=EPI_AFFINE,
+                                      relu=relu, scale=ss[0], shift=ss[1], residual=residual, out=out,
+                                      img_add=[t[3] for t in t2], out_nhw=(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1))
             return y
         raw = _library_conv(x, conv)
         return ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)

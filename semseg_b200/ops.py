@@ -102,15 +102,49 @@ def conv_taps(ksize, dilation, transpose=False):
     return taps
 
 
-def _fill_taps(desc, taps, with_wtap=True):
+def _fill_taps(desc, taps, with_wtap=True, img_add=None):
     assert 1 <= len(taps) <= MAX_TAPS
     desc.taps = len(taps)
     for i, t in enumerate(taps):
         desc.dh[i], desc.dw[i] = t[0], t[1]
         if with_wtap:
             desc.wtap[i] = t[2]
-        desc.img_add[i] = 0
+        desc.img_add[i] = img_add[i] if img_add is not None else 0
     desc.img_mul = 1
+
+
+def conv_taps_s2(ksize, n):
+    """Taps of a stride-2 'same' conv (k in {1,3}) on the 2x2 phase tensor [4N,Hh,Wh,C] (space_to_phases):
+    [(dh, dw, wtap, img_add, (ph, pw))]: input row 2*ho + r - k//2 lives in phase (r+1)&1 at row ho + dh."""
+    taps = []
+    for r in range(ksize):
+        for s in range(ksize):
+            if ksize == 3:
+                ph, dh = (0, 0) if r == 1 else (1, -1 if r == 0 else 0)
+                pw, dw = (0, 0) if s == 1 else (1, -1 if s == 0 else 0)
+            else:
+                ph = pw = dh = dw = 0
+            taps.append((dh, dw, r * ksize + s, (ph * 2 + pw) * n, (ph, pw)))
+    return taps
+
+
+def space_to_phases(x):
+    """x [N,H,W,C] bf16 -> [4N, (H+1)//2, (W+1)//2, C] (phase-major)."""
+    _require_cuda(x)
+    lib = _lib.load()
+    n, h, w, c, p = _nhwc_meta(x)
+    xp = torch.empty((4 * n, (h + 1) // 2, (w + 1) // 2, c), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.semseg_space_to_phases(_ptr(x), p, n, h, w, c, _ptr(xp), _stream()), "semseg_space_to_phases")
+    return xp
+
+
+def phases_to_space(xp, n, h, w):
+    lib = _lib.load()
+    c = xp.shape[-1]
+    assert xp.is_contiguous() and xp.shape[0] == 4 * n
+    x = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=xp.device)
+    _lib.check(lib.semseg_phases_to_space(_ptr(xp), n, h, w, c, _ptr(x), _stream()), "semseg_phases_to_space")
+    return x
 
 
 # ------------------------------------------------------------------------------------------------ conv
@@ -119,7 +153,7 @@ def conv_stats_rows(n, h, w, cout):
 
 
 def conv_fprop(x, w3d, cout, taps, *, out=None, epi=EPI_RAW, relu=False, scale=None, shift=None, residual=None,
-               stats=False, out_f32=None):
+               stats=False, out_f32=None, img_add=None, out_nhw=None):
     """Implicit-GEMM conv of NHWC bf16 `x` with packed weights `w3d` [n_wtaps][rows][cols].
 
     Returns (y, stats_partial); y is bf16 NHWC [N,H,W,cout] (or the fp32 tensor in F32 mode); stats_partial is the
@@ -127,13 +161,14 @@ def conv_fprop(x, w3d, cout, taps, *, out=None, epi=EPI_RAW, relu=False, scale=N
     """
     _require_cuda(x, w3d)
     lib = _lib.load()
-    n, h, w, cin, xp = _nhwc_meta(x)
+    nin, hin, win, cin, xp = _nhwc_meta(x)
+    n, h, w = out_nhw if out_nhw is not None else (nin, hin, win)   # output pixel grid (differs for phase tensors)
     d = ConvDesc()
     d.N, d.H, d.W, d.Cin, d.Cout = n, h, w, cin, cout
-    d.x, d.Nin, d.Hin, d.Win, d.x_pitch = x.data_ptr(), n, h, w, xp
+    d.x, d.Nin, d.Hin, d.Win, d.x_pitch = x.data_ptr(), nin, hin, win, xp
     assert w3d.dtype == torch.bfloat16 and w3d.is_contiguous() and w3d.dim() == 3
     d.w, d.n_wtaps, d.w_rows, d.w_cols = w3d.data_ptr(), w3d.shape[0], w3d.shape[1], w3d.shape[2]
-    _fill_taps(d, taps)
+    _fill_taps(d, taps, img_add=img_add)
     d.epi_mode, d.relu = epi, int(bool(relu))
     sp = None
     if epi == EPI_F32:
@@ -167,18 +202,20 @@ def conv_fprop(x, w3d, cout, taps, *, out=None, epi=EPI_RAW, relu=False, scale=N
     return y, sp
 
 
-def conv_wgrad(x, dy, cin, cout, taps, grad_out=None, accumulate=False):
-    """dW (fp32 OIHW [cout][cin][k][k]) of a stride-1 conv from NHWC bf16 x and dy."""
+def conv_wgrad(x, dy, cin, cout, taps, grad_out=None, accumulate=False, img_add=None):
+    """dW (fp32 OIHW [cout][cin][k][k]) from NHWC bf16 x and dy. The pixel grid is dy's; `x` may be a phase tensor
+    (stride-2 convs) addressed through `img_add`."""
     _require_cuda(x, dy)
     lib = _lib.load()
-    n, h, w, xc, xp = _nhwc_meta(x)
-    dn, dh_, dw_, dc, dp = _nhwc_meta(dy)
-    assert (dn, dh_, dw_) == (n, h, w) and xc >= cin and dc >= cout
+    nin, hin, win, xc, xp = _nhwc_meta(x)
+    n, h, w, dc, dp = _nhwc_meta(dy)
+    assert xc >= cin and dc >= cout
+    assert img_add is not None or (nin, hin, win) == (n, h, w)
     d = WgradDesc()
     d.N, d.H, d.W, d.Cin, d.Cout = n, h, w, cin, cout
-    d.x, d.Nin, d.Hin, d.Win, d.x_pitch = x.data_ptr(), n, h, w, xp
+    d.x, d.Nin, d.Hin, d.Win, d.x_pitch = x.data_ptr(), nin, hin, win, xp
     d.dy, d.dy_pitch = dy.data_ptr(), dp
-    _fill_taps(d, taps, with_wtap=False)
+    _fill_taps(d, taps, with_wtap=False, img_add=img_add)
     d.n_splits = 0
     splits = lib.semseg_conv_wgrad_splits(ctypes.byref(d))
     if splits <= 0:

@@ -273,6 +273,46 @@ def test_maxpool_vs_torch_with_ties():
         assert util.rel_l2(x.grad, xr.grad.permute(0, 2, 3, 1)) < 4e-3     # bf16 rounding of summed gradients only
 
 
+@pytest.mark.parametrize("case", [(2, 65, 65, 3, 64, 3), (2, 31, 31, 128, 128, 3), (2, 30, 28, 128, 128, 3),
+                                  (2, 31, 31, 256, 512, 1), (1, 119, 119, 128, 128, 3)])
+def test_stride2_conv_bn_relu_vs_torch(case):
+    """Stride-2 convs (stem conv1, layer2.0 conv2 / downsample) through the phase decomposition, fwd + bwd."""
+    from semseg_b200 import functional as SF
+    n, h, w, cin, cout, k = case
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(cin, cout, k, stride=2, padding=k // 2, bias=False).cuda()
+    bn = torch.nn.BatchNorm2d(cout).cuda()
+    torch.nn.init.uniform_(bn.weight, 0.5, 1.5)
+    torch.nn.init.normal_(bn.bias, 0, 0.2)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((n, cin, h, w), device="cuda", generator=g).to(torch.bfloat16).float()
+    xi = SF.to_nhwc_bf16(x)
+    need_dx = cin % 64 == 0
+    if need_dx:
+        xi.requires_grad_(True)
+    y = SF.conv_bn_act(xi, conv, bn, relu=True)
+    xr = x.clone().requires_grad_(True)
+    wr = conv.weight.detach().to(torch.bfloat16).float().requires_grad_(True)
+    gr, br = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+    raw = F.conv2d(xr, wr, None, 2, k // 2).to(torch.bfloat16).float()     # the kernel stores the raw output in bf16
+    raw_ = F.conv2d(xr, wr, None, 2, k // 2)
+    yr = torch.relu(F.batch_norm(raw_, None, None, gr, br, True, 0.1, 1e-5))
+    assert tuple(y.shape) == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, cout)
+    assert util.rel_l2(y, yr.permute(0, 2, 3, 1)) < 6e-3
+    gy = torch.randn(y.shape, device="cuda", generator=g).to(torch.bfloat16)
+    y.backward(gy)
+    yr.backward(gy.float().permute(0, 3, 1, 2))
+
+    def cos(a, b):
+        a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+        return float((a * b).sum() / (a.norm() * b.norm()))
+    assert util.rel_l2(conv.weight.grad, wr.grad) < 5e-2 and cos(conv.weight.grad, wr.grad) > 0.995
+    assert util.rel_l2(bn.weight.grad, gr.grad) < 5e-2 and util.rel_l2(bn.bias.grad, br.grad) < 5e-2
+    if need_dx:
+        assert util.rel_l2(xi.grad.permute(0, 3, 1, 2), xr.grad) < 5e-2
+        assert cos(xi.grad.permute(0, 3, 1, 2), xr.grad) > 0.995
+
+
 # ------------------------------------------------------------------------------------------------ blocks
 def _grad_check(model_params, oracle_sd, names, tol):
     bad = []
