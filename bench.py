@@ -173,8 +173,10 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/sec", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PSPNet50 ADE20K-shape 473x473 150 classes training step (tool/train.py:267-276), "
-                               "CPU sample of %d images/step" % args.cpu_batch},
+        "config": {"workload": "%s%d ADE20K-shape %dx%d, %d classes, synthetic training step (tool/train.py:267-276), "
+                               "%d images/GPU" % ("PSPNet" if args.arch == "psp" else "PSANet", args.layers,
+                                                  args.size, args.size, args.classes, args.batch),
+                   "sample": "CPU arm times %d images/step of that workload" % args.cpu_batch},
         "cpu_baseline": {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": "port",
                          "sample": sample},
         "e2e": {"value": r["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -296,7 +298,12 @@ def run_b200_arm(args):
         ach = flops / (t_k * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256> (cls 3x3 4096->512 fprop, bs%d %dx%d)" % (
                     args.batch, fmap, fmap), "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops"], "traffic": None, "ms_per_launch": t_k, "peak_source": pk["source"] +
+                "frac": ach / pk["bf16_tflops"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
+                # `ncu --set full` capture (profiles/r1_ncu_summary.md): 733.97 MB + 60.97 MB per launch; the
+                # algorithmic bytes are 510 MB in + 59 MB out.
+                "traffic": 794.9e6 if (args.batch, fmap) == (16, 60) else None, "traffic_unit": "bytes/launch",
+                "ms_per_launch": t_k, "peak_source": pk["source"] +
                 " burst bf16 (kernel timed alone)"}
         del xa, w, pw, flush
 

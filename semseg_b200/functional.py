@@ -50,7 +50,7 @@ def _bn_momentum(bn):
     return bn.momentum
 
 
-def _finalize_stats(stats, bn, pg):
+def _finalize_stats(stats, bn, pg, count_batches=True):
     """stats [3][C] local (mean, M2, count) -> (mean_invstd, scale_shift, world). Updates running stats."""
     world = 1
     if pg is not None:
@@ -60,7 +60,7 @@ def _finalize_stats(stats, bn, pg):
     mom = _bn_momentum(bn) if track else 0.0
     mi, ss = ops.bn_finalize(stats, bn.weight, bn.bias, bn.eps, mom, bn.running_mean if track else None,
                              bn.running_var if track else None)
-    if track and bn.num_batches_tracked is not None:
+    if count_batches and track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     return mi, ss, world
 
@@ -90,92 +90,172 @@ def _bn_backward(ctx_pg, world, dy, y, raw, mi, gamma, relu, want_dres, ss=None)
 
 
 # ------------------------------------------------------------------------------------------------ conv+bn+act
-class _ConvBnAct(torch.autograd.Function):
+class _CbaState:
+    """What one conv+BN(+residual)(+ReLU) stage keeps for its backward pass."""
+    __slots__ = ("xin", "raw", "y", "mi", "gamma", "ss", "pw", "k", "dil", "stride", "relu", "pg", "world",
+                 "in_shape", "has_res")
+
+
+def cba_forward(x, conv, bn, relu, residual, out=None):
     """conv (1x1 / 3x3; stride 1 with any dilation, or stride 2) + training BatchNorm + optional residual + ReLU.
+    Returns (y, state). Three launches: conv_fprop (raw + per-CTA statistics) -> finalise (+ SyncBN exchange) -> apply.
 
     Stride-2 convs (stem conv1, layer2.0 conv2 / downsample — model/resnet.py:108,130-137) run on the same
     stride-1 tensor-core kernel through a 2x2 phase decomposition of the input (ops.space_to_phases): tap (r, s)
     reads phase ((r+1)&1, (s+1)&1) shifted by -1 or 0; dgrad is one small conv per phase, wgrad reads the phases."""
+    pw = packed(conv)
+    k, dil, stride = conv.kernel_size[0], conv.dilation[0], conv.stride[0]
+    n, h, w, cx = x.shape
+    if stride == 1:
+        xin, img_add, out_nhw = x, None, None
+        taps = ops.conv_taps(k, dil)
+    else:
+        xin = ops.space_to_phases(x)                     # [4N, Hh, Wh, C]
+        t2 = ops.conv_taps_s2(k, n)
+        taps, img_add = [t[:3] for t in t2], [t[3] for t in t2]
+        out_nhw = (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1)
+    raw, sp = ops.conv_fprop(xin, pw.wf, pw.cout, taps, stats=True, img_add=img_add, out_nhw=out_nhw)
+    pg = _sync_group(bn)
+    track = bn.track_running_stats and bn.running_mean is not None
+    mom = _bn_momentum(bn) if track else 0.0
+    rm, rv = (bn.running_mean, bn.running_var) if track else (None, None)
+    px = p2p.get_exchange(pg) if pg is not None else None
+    if pg is None:
+        # single rank: merge the per-CTA partials and finalise in one launch
+        mi, ss = ops.bn_finalize_partials(sp, bn.weight, bn.bias, bn.eps, mom, rm, rv)
+        world = 1
+    elif px is not None and 3 * pw.cout <= p2p.SLOT_FLOATS:
+        # SyncBN: statistics exchanged over NVLink peer memory inside the finalise kernel (no NCCL call)
+        mi, ss = ops.bn_finalize_p2p(sp, bn.weight, bn.bias, bn.eps, mom, rm, rv, px)
+        world = px.world
+    else:
+        mi, ss, world = _finalize_stats(ops.bn_merge_partials(sp), bn, pg, count_batches=False)
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    y = ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)
+    st = _CbaState()
+    # ReLU mask for backward: with a residual it needs the saved output, otherwise it is recomputed from raw
+    need_y = relu and residual is not None
+    st.xin, st.raw, st.y, st.mi, st.gamma = xin, raw, (y if need_y else None), mi, bn.weight
+    st.ss = ss if (relu and not need_y) else None
+    st.pw, st.k, st.dil, st.stride, st.relu, st.pg, st.world = pw, k, dil, stride, relu, pg, world
+    st.in_shape, st.has_res = (n, h, w, cx), residual is not None
+    return y, st
+
+
+def cba_backward(st, dy, need_dx=True, need_dw=True, need_dres=False, dx_add=None):
+    """Backward of cba_forward: returns (dx, dw, dgamma, dbeta, dres). `dx_add` (same shape as dx) is summed into
+    dx inside the dgrad epilogue (AFFINE mode with a residual operand) — this is how gradient fan-in is fused."""
+    pw = st.pw
+    n, h, w, cx = st.in_shape
+    d_raw, dres, dgamma, dbeta = _bn_backward(st.pg, st.world, dy, st.y, st.raw, st.mi, st.gamma, st.relu,
+                                              st.has_res and need_dres, st.ss)
+    dx = dw = None
+    if st.stride == 1:
+        if need_dx:
+            if dx_add is not None:
+                dx, _ = ops.conv_fprop(d_raw, pw.wd, pw.cin, ops.conv_taps(st.k, st.dil, transpose=True),
+                                       epi=EPI_AFFINE, residual=dx_add)
+            else:
+                dx, _ = ops.conv_fprop(d_raw, pw.wd, pw.cin, ops.conv_taps(st.k, st.dil, transpose=True))
+        if need_dw:
+            dw = ops.conv_wgrad(st.xin, d_raw, cx, pw.cout, ops.conv_taps(st.k, st.dil))
+    else:
+        t2 = ops.conv_taps_s2(st.k, n)
+        if need_dx:
+            if pw.cin % 64 != 0:
+                raise NotImplementedError("semseg_b200: input gradient of a stride-2 conv needs Cin % 64 == 0")
+            hh, wh = st.xin.shape[1], st.xin.shape[2]
+            dxp = torch.empty((4 * n, hh, wh, pw.cin), dtype=torch.bfloat16, device=dy.device)
+            for q in range(4):
+                sub = [(-t[0], -t[1], t[2]) for t in t2 if t[4] == (q >> 1, q & 1)]
+                if sub:      # dx of phase q: conv of d_raw with the taps that read this phase (mirrored shifts)
+                    ops.conv_fprop(d_raw, pw.wd, pw.cin, sub, out=dxp[q * n:(q + 1) * n], out_nhw=(n, hh, wh))
+                else:
+                    dxp[q * n:(q + 1) * n].zero_()
+            dx = ops.phases_to_space(dxp, n, h, w)
+            if dx_add is not None:
+                dx = ops.add_bf16(dx, dx_add)
+        if need_dw:
+            dw = ops.conv_wgrad(st.xin, d_raw, cx, pw.cout, [t[:2] for t in t2], img_add=[t[3] for t in t2])
+    if dw is not None and cx != pw.cin:
+        dw = dw[:, :pw.cin].contiguous()          # input channels were zero-padded to a multiple of 8 (stem)
+    return dx, dw, dgamma, dbeta, dres
+
+
+class _ConvBnAct(torch.autograd.Function):
+    """Autograd wrapper of one cba_forward / cba_backward stage."""
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, conv, bn, relu, out):
-        pw = packed(conv)
-        k, dil, stride = conv.kernel_size[0], conv.dilation[0], conv.stride[0]
-        n, h, w, cx = x.shape
-        if stride == 1:
-            xin, img_add, out_nhw = x, None, None
-            taps = ops.conv_taps(k, dil)
-        else:
-            xin = ops.space_to_phases(x)                     # [4N, Hh, Wh, C]
-            t2 = ops.conv_taps_s2(k, n)
-            taps, img_add = [t[:3] for t in t2], [t[3] for t in t2]
-            out_nhw = (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1)
-        raw, sp = ops.conv_fprop(xin, pw.wf, pw.cout, taps, stats=True, img_add=img_add, out_nhw=out_nhw)
-        pg = _sync_group(bn)
-        if pg is None:
-            # single rank: merge the per-CTA partials and finalise in one launch
-            track = bn.track_running_stats and bn.running_mean is not None
-            mi, ss = ops.bn_finalize_partials(sp, bn.weight, bn.bias, bn.eps, _bn_momentum(bn) if track else 0.0,
-                                              bn.running_mean if track else None, bn.running_var if track else None)
-            if track and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked.add_(1)
-            world = 1
-        else:
-            px = p2p.get_exchange(pg)
-            if px is not None and 3 * pw.cout <= p2p.SLOT_FLOATS:
-                # statistics exchanged over NVLink peer memory inside the finalise kernel (no NCCL call)
-                track = bn.track_running_stats and bn.running_mean is not None
-                mi, ss = ops.bn_finalize_p2p(sp, bn.weight, bn.bias, bn.eps, _bn_momentum(bn) if track else 0.0,
-                                             bn.running_mean if track else None,
-                                             bn.running_var if track else None, px)
-                if track and bn.num_batches_tracked is not None:
-                    bn.num_batches_tracked.add_(1)
-                world = px.world
-            else:
-                mi, ss, world = _finalize_stats(ops.bn_merge_partials(sp), bn, pg)
-        y = ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)
-        # ReLU mask for backward: with a residual it needs the saved output, otherwise it is recomputed from raw
-        need_y = relu and residual is not None
-        ctx.save_for_backward(xin, raw, y if need_y else None, mi, gamma, ss if (relu and not need_y) else None)
-        ctx.pw, ctx.k, ctx.dil, ctx.stride, ctx.relu, ctx.pg, ctx.world = pw, k, dil, stride, relu, pg, world
-        ctx.in_shape = (n, h, w, cx)
-        ctx.has_res = residual is not None
+        y, st = cba_forward(x, conv, bn, relu, residual, out)
+        ctx.st = st
         if out is not None:
             ctx.mark_dirty(out)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xin, raw, y, mi, gamma, ss = ctx.saved_tensors
-        pw = ctx.pw
-        n, h, w, cx = ctx.in_shape
-        d_raw, dres, dgamma, dbeta = _bn_backward(ctx.pg, ctx.world, dy, y, raw, mi, gamma, ctx.relu,
-                                                  ctx.has_res and ctx.needs_input_grad[4], ss)
-        dx = dw = None
-        if ctx.stride == 1:
-            if ctx.needs_input_grad[0]:
-                dx, _ = ops.conv_fprop(d_raw, pw.wd, pw.cin, ops.conv_taps(ctx.k, ctx.dil, transpose=True))
-            if ctx.needs_input_grad[1]:
-                dw = ops.conv_wgrad(xin, d_raw, cx, pw.cout, ops.conv_taps(ctx.k, ctx.dil))
-        else:
-            t2 = ops.conv_taps_s2(ctx.k, n)
-            if ctx.needs_input_grad[0]:
-                if pw.cin % 64 != 0:
-                    raise NotImplementedError("semseg_b200: input gradient of a stride-2 conv needs Cin % 64 == 0")
-                hh, wh = xin.shape[1], xin.shape[2]
-                dxp = torch.empty((4 * n, hh, wh, pw.cin), dtype=torch.bfloat16, device=dy.device)
-                for q in range(4):
-                    sub = [(-t[0], -t[1], t[2]) for t in t2 if t[4] == (q >> 1, q & 1)]
-                    if sub:      # dx of phase q: conv of d_raw with the taps that read this phase (mirrored shifts)
-                        ops.conv_fprop(d_raw, pw.wd, pw.cin, sub, out=dxp[q * n:(q + 1) * n], out_nhw=(n, hh, wh))
-                    else:
-                        dxp[q * n:(q + 1) * n].zero_()
-                dx = ops.phases_to_space(dxp, n, h, w)
-            if ctx.needs_input_grad[1]:
-                dw = ops.conv_wgrad(xin, d_raw, cx, pw.cout, [t[:2] for t in t2], img_add=[t[3] for t in t2])
-        if dw is not None and cx != pw.cin:
-            dw = dw[:, :pw.cin].contiguous()          # input channels were zero-padded to a multiple of 8 (stem)
+        ni = ctx.needs_input_grad
+        dx, dw, dgamma, dbeta, dres = cba_backward(ctx.st, dy, need_dx=ni[0], need_dw=ni[1], need_dres=ni[4])
+        ctx.st = None
         return dx, dw, dgamma, dbeta, dres, None, None, None, None
+
+
+class _BottleneckFn(torch.autograd.Function):
+    """A whole Bottleneck (model/resnet.py:74-94) as one autograd node: conv1-bn1-relu, conv2-bn2-relu, conv3-bn3,
+    (+ downsample conv-bn), residual add, relu. Besides saving three autograd nodes per block, the backward pass
+    fuses the gradient fan-in (dx = dgrad(conv1) + d(residual branch)) into the dgrad epilogue instead of a separate
+    elementwise add."""
+
+    @staticmethod
+    def forward(ctx, x, blk, *params):
+        y1, s1 = cba_forward(x, blk.conv1, blk.bn1, True, None)
+        y2, s2 = cba_forward(y1, blk.conv2, blk.bn2, True, None)
+        if blk.downsample is not None:
+            res, sd = cba_forward(x, blk.downsample[0], blk.downsample[1], False, None)
+        else:
+            res, sd = x, None
+        y3, s3 = cba_forward(y2, blk.conv3, blk.bn3, True, res)
+        ctx.states = (s1, s2, s3, sd)
+        return y3
+
+    @staticmethod
+    def backward(ctx, dy):
+        s1, s2, s3, sd = ctx.states
+        ctx.states = None
+        need_dx = ctx.needs_input_grad[0]
+        d2, dw3, dg3, db3, dres = cba_backward(s3, dy, need_dres=True)
+        d1, dw2, dg2, db2, _ = cba_backward(s2, d2)
+        grads_ds = ()
+        if sd is not None:
+            dxd, dwd, dgd, dbd, _ = cba_backward(sd, dres, need_dx=need_dx)
+            dres_to_x = dxd
+            grads_ds = (dwd, dgd, dbd)
+        else:
+            dres_to_x = dres
+        dx, dw1, dg1, db1, _ = cba_backward(s1, d1, need_dx=need_dx, dx_add=dres_to_x if need_dx else None)
+        return (dx, None, dw1, dg1, db1, dw2, dg2, db2, dw3, dg3, db3) + grads_ds
+
+
+def bottleneck(x, blk):
+    """Fused Bottleneck when every stage is covered by the native kernels in training mode, else stage by stage."""
+    convs = [blk.conv1, blk.conv2, blk.conv3] + ([blk.downsample[0]] if blk.downsample is not None else [])
+    bns = [blk.bn1, blk.bn2, blk.bn3] + ([blk.downsample[1]] if blk.downsample is not None else [])
+    cins = [x.shape[-1], blk.conv1.out_channels, blk.conv2.out_channels, x.shape[-1]]
+    fused = (torch.is_grad_enabled() and all(b.training or b.running_mean is None for b in bns) and
+             all(_is_native_conv(c, ci) for c, ci in zip(convs, cins)) and
+             (blk.downsample is None or len(blk.downsample) == 2))
+    if fused:
+        params = [blk.conv1.weight, blk.bn1.weight, blk.bn1.bias, blk.conv2.weight, blk.bn2.weight, blk.bn2.bias,
+                  blk.conv3.weight, blk.bn3.weight, blk.bn3.bias]
+        if blk.downsample is not None:
+            params += [blk.downsample[0].weight, blk.downsample[1].weight, blk.downsample[1].bias]
+        return _BottleneckFn.apply(x, blk, *params)
+    y = conv_bn_act(x, blk.conv1, blk.bn1, relu=True)
+    y = conv_bn_act(y, blk.conv2, blk.bn2, relu=True)
+    residual = conv_bn_act(x, blk.downsample[0], blk.downsample[1], relu=False) if blk.downsample is not None else x
+    return conv_bn_act(y, blk.conv3, blk.bn3, relu=True, residual=residual)
 
 
 class _BnAct(torch.autograd.Function):

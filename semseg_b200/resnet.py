@@ -54,14 +54,8 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
         self.stride = stride
 
-    def forward_nhwc(self, x, out=None):
-        y = SF.conv_bn_act(x, self.conv1, self.bn1, relu=True)
-        y = SF.conv_bn_act(y, self.conv2, self.bn2, relu=True)
-        if self.downsample is not None:
-            residual = SF.conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False)
-        else:
-            residual = x
-        return SF.conv_bn_act(y, self.conv3, self.bn3, relu=True, residual=residual, out=out)
+    def forward_nhwc(self, x):
+        return SF.bottleneck(x, self)
 
     def forward(self, x):
         from . import ops
