@@ -215,11 +215,11 @@ int semseg_add_bf16(const void* a, int a_pitch, const void* b, int b_pitch, void
 
 /* ------------------------------------------------------------------------------------------------
  * nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC bf16 (model/resnet.py:115): y [N,Ho,Wo,C] with
- * Ho = (H-1)/2+1. Backward re-derives the arg-max (first maximum in window order, as ATen) and gathers:
- * dx [N,H,W,C] dense, deterministic, no index tensor.
+ * Ho = (H-1)/2+1; argcode uint8 [N,Ho,Wo,C] (or NULL) = window position 0..8 of the arg-max (first maximum in window
+ * order, as ATen). Backward gathers with those codes: dx [N,H,W,C] dense, deterministic, no atomics.
  */
-int semseg_maxpool3x3s2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
-int semseg_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+int semseg_maxpool3x3s2_fwd(const void* x, void* y, void* argcode, int N, int H, int W, int C, void* stream);
+int semseg_maxpool3x3s2_bwd(const void* argcode, const void* dy, void* dx, int N, int H, int W, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pyramid pooling module data movement (model/pspnet.py:12-26), NHWC bf16, all bins in one launch.

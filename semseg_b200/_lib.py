@@ -94,7 +94,7 @@ SIGNATURES = {
                                     c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     "semseg_relu_bwd": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp]),
     "semseg_add_bf16": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp]),
-    "semseg_maxpool3x3s2_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_maxpool3x3s2_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_maxpool3x3s2_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_ppm_pool": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "semseg_ppm_pool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),

@@ -1,8 +1,8 @@
 // MaxPool2d(kernel 3, stride 2, padding 1) on NHWC bf16 (model/resnet.py:115, used as layer0[9]).
-// Forward: one thread per (output pixel, 8 channels). Backward is a deterministic gather: every input pixel
-// re-derives, for the (up to four) windows that contain it, whether it is that window's arg-max (first maximum in
-// row-major window order, the tie rule of ATen's max_pool2d_with_indices) and sums the matching dy. No index tensor,
-// no atomics, every dx element written once.
+// Forward: one thread per (output pixel, 8 channels); it also records the window position (0..8) of the arg-max
+// (first maximum in row-major window order, the tie rule of ATen's max_pool2d_with_indices) as one byte per element.
+// Backward is a deterministic gather: every input pixel checks the (up to four) windows that contain it and sums the
+// dy of those whose recorded arg-max is this pixel. No atomics, every dx element written once.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -27,8 +27,9 @@ __device__ __forceinline__ void mp_st8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = o;
 }
 
-__global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
-                                        int H, int W, int C, int Ho, int Wo) {
+__global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                        unsigned char* __restrict__ argcode, int N, int H, int W, int C, int Ho,
+                                        int Wo) {
   const int groups = C >> 3;
   const long long total = static_cast<long long>(N) * Ho * Wo * groups;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -40,8 +41,12 @@ __global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __n
     const int ho = static_cast<int>(p % Ho);
     const int n = static_cast<int>(p / Ho);
     float m[8];
+    unsigned code[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+    for (int q = 0; q < 8; ++q) {
+      m[q] = -INFINITY;
+      code[q] = 255u;
+    }
     for (int kh = 0; kh < 3; ++kh) {
       const int h = 2 * ho - 1 + kh;
       if (h < 0 || h >= H) continue;
@@ -51,14 +56,26 @@ __global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __n
         float f[8];
         mp_ld8(x + ((static_cast<size_t>(n) * H + h) * W + w) * C + c0, f);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], f[q]);
+        for (int q = 0; q < 8; ++q) {
+          if (f[q] > m[q] || code[q] == 255u) {  // first maximum in row-major window order (ATen's tie rule)
+            m[q] = f[q];
+            code[q] = static_cast<unsigned>(kh * 3 + kw);
+          }
+        }
       }
     }
-    mp_st8(y + ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c0, m);
+    const size_t o = ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c0;
+    mp_st8(y + o, m);
+    if (argcode) {
+      uint2 pk;
+      pk.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+      pk.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+      *reinterpret_cast<uint2*>(argcode + o) = pk;
+    }
   }
 }
 
-__global__ void maxpool3x3s2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+__global__ void maxpool3x3s2_bwd_kernel(const unsigned char* __restrict__ argcode, const __nv_bfloat16* __restrict__ dy,
                                         __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
   const int groups = C >> 3;
   const long long total = static_cast<long long>(N) * H * W * groups;
@@ -72,42 +89,20 @@ __global__ void maxpool3x3s2_bwd_kernel(const __nv_bfloat16* __restrict__ x, con
     const int n = static_cast<int>(p / H);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // windows containing (h, w): ho with 2*ho-1 <= h <= 2*ho+1
-    const int ho_lo = max((h) / 2, 0), ho_hi = min((h + 1) / 2, Ho - 1);
-    const int wo_lo = max((w) / 2, 0), wo_hi = min((w + 1) / 2, Wo - 1);
-    const __nv_bfloat16* xn = x + static_cast<size_t>(n) * H * W * C + c0;
+    const int ho_lo = h / 2, ho_hi = min((h + 1) / 2, Ho - 1);
+    const int wo_lo = w / 2, wo_hi = min((w + 1) / 2, Wo - 1);
     for (int ho = ho_lo; ho <= ho_hi; ++ho) {
       for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-        // first maximum in row-major order over the valid window positions
-        float best[8];
-        int arg[8];
+        const unsigned me = static_cast<unsigned>((h - (2 * ho - 1)) * 3 + (w - (2 * wo - 1)));  // my code in this window
+        const size_t o = ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c0;
+        const uint2 pk = *reinterpret_cast<const uint2*>(argcode + o);
+        float g[8];
+        mp_ld8(dy + o, g);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          best[q] = -INFINITY;
-          arg[q] = -1;
+          const unsigned cq = ((q < 4 ? pk.x : pk.y) >> ((q & 3) * 8)) & 0xffu;
+          if (cq == me) acc[q] += g[q];
         }
-        for (int kh = 0; kh < 3; ++kh) {
-          const int hh = 2 * ho - 1 + kh;
-          if (hh < 0 || hh >= H) continue;
-          for (int kw = 0; kw < 3; ++kw) {
-            const int ww = 2 * wo - 1 + kw;
-            if (ww < 0 || ww >= W) continue;
-            float f[8];
-            mp_ld8(xn + (static_cast<size_t>(hh) * W + ww) * C, f);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (f[q] > best[q] || arg[q] < 0) {
-                best[q] = f[q];
-                arg[q] = hh * W + ww;
-              }
-            }
-          }
-        }
-        float g[8];
-        mp_ld8(dy + ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c0, g);
-        const int me = h * W + w;
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (arg[q] == me) acc[q] += g[q];
       }
     }
     mp_st8(dx + ((static_cast<size_t>(n) * H + h) * W + w) * C + c0, acc);
@@ -124,24 +119,27 @@ static int mp_blocks(long long total) {
 
 using namespace sb;
 
-extern "C" int semseg_maxpool3x3s2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream_) {
+extern "C" int semseg_maxpool3x3s2_fwd(const void* x, void* y, void* argcode, int N, int H, int W, int C,
+                                       void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool_fwd: bad args");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
   maxpool3x3s2_fwd_kernel<<<mp_blocks(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
-                                                               static_cast<__nv_bfloat16*>(y), N, H, W, C, Ho, Wo);
+                                                               static_cast<__nv_bfloat16*>(y),
+                                                               static_cast<unsigned char*>(argcode), N, H, W, C, Ho,
+                                                               Wo);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
 
-extern "C" int semseg_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C,
+extern "C" int semseg_maxpool3x3s2_bwd(const void* argcode, const void* dy, void* dx, int N, int H, int W, int C,
                                        void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SB_CHECK_ARG(x && dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool_bwd: bad args");
+  SB_CHECK_ARG(argcode && dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool_bwd: bad args");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(N) * H * W * (C / 8);
-  maxpool3x3s2_bwd_kernel<<<mp_blocks(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
+  maxpool3x3s2_bwd_kernel<<<mp_blocks(total), 256, 0, stream>>>(static_cast<const unsigned char*>(argcode),
                                                                static_cast<const __nv_bfloat16*>(dy),
                                                                static_cast<__nv_bfloat16*>(dx), N, H, W, C, Ho, Wo);
   SB_LAUNCHED();

@@ -462,13 +462,15 @@ def dropout2d_nhwc(x, p, training):
 class _MaxPool3x3s2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        ctx.save_for_backward(x)
-        return ops.maxpool3x3s2_fwd(x)
+        y, code = ops.maxpool3x3s2_fwd(x, want_argcode=True)
+        ctx.save_for_backward(code)
+        ctx.in_shape = tuple(x.shape)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
-        return ops.maxpool3x3s2_bwd(x, dy)
+        (code,) = ctx.saved_tensors
+        return ops.maxpool3x3s2_bwd(code, dy, ctx.in_shape)
 
 
 def _pair(v):

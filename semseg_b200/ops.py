@@ -487,22 +487,26 @@ def ppm_upsample_bwd(dout, c_off, bins, cr):
 
 
 # ------------------------------------------------------------------------------------------------ max pool
-def maxpool3x3s2_fwd(x):
+def maxpool3x3s2_fwd(x, want_argcode=True):
+    """-> (y, argcode uint8 or None)."""
     _require_cuda(x)
     lib = _lib.load()
     n, h, w, c, p = _nhwc_meta(x)
     assert p == c, "maxpool expects a dense NHWC tensor"
-    y = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.semseg_maxpool3x3s2_fwd(_ptr(x), _ptr(y), n, h, w, c, _stream()), "semseg_maxpool3x3s2_fwd")
-    return y
+    shape = (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c)
+    y = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    code = torch.empty(shape, dtype=torch.uint8, device=x.device) if want_argcode else None
+    _lib.check(lib.semseg_maxpool3x3s2_fwd(_ptr(x), _ptr(y), _ptr(code), n, h, w, c, _stream()),
+               "semseg_maxpool3x3s2_fwd")
+    return y, code
 
 
-def maxpool3x3s2_bwd(x, dy):
+def maxpool3x3s2_bwd(argcode, dy, in_shape):
     lib = _lib.load()
-    n, h, w, c, _ = _nhwc_meta(x)
+    n, h, w, c = in_shape
     dy = dy.contiguous()
-    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.semseg_maxpool3x3s2_bwd(_ptr(x), _ptr(dy), _ptr(dx), n, h, w, c, _stream()),
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
+    _lib.check(lib.semseg_maxpool3x3s2_bwd(_ptr(argcode), _ptr(dy), _ptr(dx), n, h, w, c, _stream()),
                "semseg_maxpool3x3s2_bwd")
     return dx
 
