@@ -435,6 +435,32 @@ def test_pspnet50_config2_shape_train_step_loss_parity():
     assert tuple(r["out"].shape) == (2, 473, 473) and r["out"].dtype == torch.int64
 
 
+def test_psanet50_config3_shape_train_step_loss_parity():
+    """BASELINE config 3 per-GPU shard: PSANet50, 465x465 (59x59 maps, 30x30 attention, 59x59 mask), 2 images."""
+    r = _run_net("psa", 465, 150, 2, None, None)
+    assert r["eval_rel_l2"] < 2e-2, r["eval_rel_l2"]
+    assert abs(r["main"][0] - r["main"][1]) < 2e-3 * r["main"][1]
+    assert abs(r["aux"][0] - r["aux"][1]) < 2e-3 * r["aux"][1]
+    _grad_sanity(r)
+
+
+def test_pspnet101_config4_shape_train_step_loss_parity():
+    """BASELINE config 4 per-GPU shard: PSPNet101, Cityscapes shape 713x713 (90x90 maps), 19 classes, 2 images."""
+    build = util.build_pspnet
+    model = build(101, 19).cuda()
+    orc, sd = util.oracle_from(model, "psp", layers=101, classes=19)
+    x, y = util.synth(2, 713, 713, 19, device="cuda")
+    model.train()
+    orc.train()
+    out, ml, al = model(x, y)
+    (ml + 0.4 * al).backward()
+    oo, mlo, alo = orc.forward(x, y)
+    assert abs(ml.item() - mlo.item()) < 2e-3 * mlo.item()
+    assert abs(al.item() - alo.item()) < 2e-3 * alo.item()
+    assert tuple(out.shape) == (2, 713, 713)
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+
+
 def test_state_dict_round_trip_with_oracle_weights():
     m = util.build_pspnet(50, 21).cuda()
     sd = m.state_dict()
