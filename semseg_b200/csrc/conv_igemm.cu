@@ -56,12 +56,29 @@ struct ConvKParams {
   float* stats_partial;  // [gridDim.x][3][Cout]: per-CTA (sum, sum of squares, count) per output channel
 };
 
-template <int BLOCK_N>
+// kCluster: CTAs run as clusters of two that work on two neighbouring pixel tiles of the SAME channel block; each CTA
+// loads half of the weight tile and TMA-multicasts it into both CTAs' shared memory, so the weight operand crosses
+// L2->SM once per pair (per-CTA operand traffic per K block: 16 KB + 16 KB instead of 16 KB + 32 KB at BLOCK_N=256).
+// The two CTAs stay in lock-step per smem stage: a stage is refilled only after BOTH MMA warps released it
+// (tcgen05.commit multicast onto both CTAs' empty barriers).
+template <int BLOCK_N, bool kCluster>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
+  const uint32_t cta_rank = kCluster ? cluster_ctarank() : 0u;
+  // Work items: (pixel tile, channel tile) or, clustered, (pair of pixel tiles, channel tile) per cluster.
+  const int item_first = kCluster ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_step = kCluster ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_items = (kCluster ? ((p.num_m_tiles + 1) >> 1) : p.num_m_tiles) * p.n_tiles;
+  auto decode_item = [&](int item, int& m_tile, int& n_tile) -> bool {
+    n_tile = item % p.n_tiles;
+    const int mi = item / p.n_tiles;
+    const int m_raw = kCluster ? 2 * mi + static_cast<int>(cta_rank) : mi;
+    m_tile = m_raw < p.num_m_tiles ? m_raw : p.num_m_tiles - 1;  // odd tail: the second CTA shadows the last tile
+    return m_raw < p.num_m_tiles;
+  };
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,7 +95,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.n_tiles;
   const int num_kb = p.taps * p.k_chunks;
   const uint32_t a_bytes = static_cast<uint32_t>(p.bh * p.bw) * 128u;
   const uint32_t stage_tx = a_bytes + static_cast<uint32_t>(Cfg::kBTileBytes);
@@ -89,7 +105,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmC);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], kCluster ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -106,6 +122,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -113,9 +130,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================================================================== TMA producer
     if (elect_one()) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
+      for (int item = item_first; item < num_items; item += item_step) {
+        int m_tile, n_tile;
+        decode_item(item, m_tile, n_tile);
         const int tiles_per_img = p.tiles_h * p.tiles_w;
         const int img = m_tile / tiles_per_img;
         const int rem = m_tile - img * tiles_per_img;
@@ -134,12 +151,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_load_4d(a_dst, &tmA, &full_bar[s], cb * kBlockK, w0 + p.dw[t], h0 + p.dh[t],
                       img * p.img_mul + p.img_add[t]);
           // 3-D weights [taps][rows][cols]: coordinates (k, row, tap)
-          asm volatile(
-              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
-              "%5}], [%2];" ::"r"(smem_u32(b_dst)),
-              "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[s])), "r"(cb * kBlockK), "r"(n0),
-              "r"(p.wtap[t])
-              : "memory");
+          if (kCluster) {
+            // my half of the weight rows, multicast into both CTAs (each CTA's full barrier expects the whole tile)
+            constexpr int kHalfRows = BLOCK_N / 2;
+            tma_load_3d_mcast(b_dst + cta_rank * (Cfg::kBTileBytes / 2), &tmB, &full_bar[s], cb * kBlockK,
+                              n0 + static_cast<int>(cta_rank) * kHalfRows, p.wtap[t], static_cast<uint16_t>(3));
+          } else {
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+                "%5}], [%2];" ::"r"(smem_u32(b_dst)),
+                "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[s])), "r"(cb * kBlockK), "r"(n0),
+                "r"(p.wtap[t])
+                : "memory");
+          }
         }
       }
     }
@@ -149,7 +173,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
       int it = 0;
       int tile_iter = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+      for (int item = item_first; item < num_items; item += item_step, ++tile_iter) {
         const int as = tile_iter & 1;
         const uint32_t apar = (tile_iter >> 1) & 1;
         mbar_wait(&tmem_empty[as], apar ^ 1);
@@ -170,7 +194,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
                       (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage once these MMAs have read it (clustered: in both CTAs, the peer multicasts into it)
+          if (kCluster) umma_commit_mcast(&empty_bar[s], static_cast<uint16_t>(3));
+          else umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full[as]);  // accumulator complete
       }
@@ -182,9 +208,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int et = (warp - 2) * 32 + lane;  // 0..127
     int tile_iter = 0;
     int store_buf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+    for (int item = item_first; item < num_items; item += item_step, ++tile_iter) {
+      int m_tile, n_tile;
+      const bool tile_live = decode_item(item, m_tile, n_tile);
+      if (!tile_live) {  // shadow tile of an odd tail: keep the TMEM handshake, store nothing
+        const int as_ = tile_iter & 1;
+        mbar_wait(&tmem_full[as_], (tile_iter >> 1) & 1);
+        tc_fence_after();
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[as_]);
+        continue;
+      }
       const int tiles_per_img = p.tiles_h * p.tiles_w;
       const int img = m_tile / tiles_per_img;
       const int rem = m_tile - img * tiles_per_img;
@@ -363,25 +397,65 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();  // the peer may still signal my barriers until it is done as well
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
+static bool cluster_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEMSEG_B200_CLUSTER");
+    v = (e && e[0] == '1') ? 1 : 0;  // opt-in until validated on hardware
+  }
+  return v != 0;
+}
+
+// Grid (= rows of the statistics buffer) and whether the clustered variant is used.
+static int conv_grid(int num_m_tiles, int n_tiles, bool* clustered) {
+  const int sms = num_sms();
+  const bool cl = cluster_enabled() && num_m_tiles >= 2;
+  *clustered = cl;
+  if (!cl) {
+    const long long tiles = static_cast<long long>(num_m_tiles) * n_tiles;
+    return static_cast<int>(tiles < sms ? tiles : sms);
+  }
+  const long long items = static_cast<long long>((num_m_tiles + 1) / 2) * n_tiles;  // one per cluster
+  const long long max_clusters = sms / 2;
+  return static_cast<int>(2 * (items < max_clusters ? items : max_clusters));
+}
+
 template <int BLOCK_N>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvKParams& kp,
-                       cudaStream_t stream) {
+                       bool clustered, int grid, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
+    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int num_tiles = kp.num_m_tiles * kp.n_tiles;
-  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  conv_igemm_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, kp);
+  if (!clustered) {
+    conv_igemm_kernel<BLOCK_N, false><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, kp);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, true>, tmA, tmB, tmC, kp));
+  }
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
@@ -398,10 +472,8 @@ extern "C" int semseg_conv_stats_rows(int N, int H, int W, int Cout) {
   if (N <= 0 || H <= 0 || W <= 0 || Cout <= 0) return SEMSEG_E_INVALID;
   int bh, bw;
   sb::choose_box(H, W, sb::kBlockM, &bh, &bw);
-  const long long tiles =
-      static_cast<long long>(N) * sb::cdiv(H, bh) * sb::cdiv(W, bw) * sb::cdiv(Cout, conv_block_n(Cout));
-  const int sms = sb::num_sms();
-  return static_cast<int>(tiles < sms ? tiles : sms);
+  bool clustered;
+  return sb::conv_grid(N * sb::cdiv(H, bh) * sb::cdiv(W, bw), sb::cdiv(Cout, conv_block_n(Cout)), &clustered);
 }
 
 extern "C" int semseg_conv_fprop(const semseg_conv_desc* d, void* stream_) {
@@ -438,6 +510,8 @@ extern "C" int semseg_conv_fprop(const semseg_conv_desc* d, void* stream_) {
 
   const int block_n = conv_block_n(d->Cout);
   kp.n_tiles = cdiv(d->Cout, block_n);
+  bool clustered = false;
+  const int grid = conv_grid(kp.num_m_tiles, kp.n_tiles, &clustered);
 
   // A: input activations [Nin][Hin][Win][x_pitch] viewed as (C, W, H, N)
   CUtensorMap tmA, tmB, tmC;
@@ -452,7 +526,8 @@ extern "C" int semseg_conv_fprop(const semseg_conv_desc* d, void* stream_) {
   {
     uint64_t dims[3] = {(uint64_t)d->w_cols, (uint64_t)d->w_rows, (uint64_t)d->n_wtaps};
     uint64_t str[2] = {(uint64_t)d->w_cols * 2, (uint64_t)d->w_cols * 2 * d->w_rows};
-    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)block_n, 1};
+    // clustered: each CTA loads (and multicasts) half of the weight rows of the tile
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)(clustered ? block_n / 2 : block_n), 1};
     int r = encode_tmap_bf16(&tmB, d->w, 3, dims, str, box);
     if (r) return r;
   }
@@ -472,8 +547,8 @@ extern "C" int semseg_conv_fprop(const semseg_conv_desc* d, void* stream_) {
     if (r) return r;
   }
   switch (block_n) {
-    case 256: return launch_conv<256>(tmA, tmB, tmC, kp, stream);
-    case 128: return launch_conv<128>(tmA, tmB, tmC, kp, stream);
-    default: return launch_conv<64>(tmA, tmB, tmC, kp, stream);
+    case 256: return launch_conv<256>(tmA, tmB, tmC, kp, clustered, grid, stream);
+    case 128: return launch_conv<128>(tmA, tmB, tmC, kp, clustered, grid, stream);
+    default: return launch_conv<64>(tmA, tmB, tmC, kp, clustered, grid, stream);
   }
 }
