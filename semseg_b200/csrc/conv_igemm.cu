@@ -257,6 +257,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           st_old[4] = st_dst[2 * p.Cout];
           st_old[5] = st_dst[2 * p.Cout + 1];
         }
+        // Residual operand (AFFINE mode): issue the row's eight 16-byte loads before the TMEM loads so their latency
+        // overlaps with tcgen05.ld instead of sitting in front of the first use.
+        uint4 rres[8];
+        const bool has_res = p.epi_mode == SEMSEG_EPI_AFFINE && p.residual != nullptr && row_valid;
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_pitch + c0);
+#pragma unroll
+          for (int j8 = 0; j8 < 8; ++j8) rres[j8] = rp[j8];
+        }
         uint32_t v[2][32];
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(g * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N + ch * 64);
@@ -281,12 +290,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
 
         if (p.epi_mode == SEMSEG_EPI_AFFINE) {
-          const __nv_bfloat16* rrow = (p.residual && row_valid) ? p.residual + pix * p.res_pitch + c0 : nullptr;
 #pragma unroll
           for (int j8 = 0; j8 < 8; ++j8) {
             float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (rrow) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + j8 * 8);
+            if (has_res) {
+              const uint4 rv = rres[j8];
               const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
