@@ -35,6 +35,9 @@ struct ConvCfg {
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStageOutBytes + kMiscBytes + 1024;
+  // CTA-pair mode: each CTA stages its own 128 pixel rows of A and HALF of the weight rows -> smaller stages, more of them
+  static constexpr int kPairStageBytes = kATileBytes + kBTileBytes / 2;
+  static constexpr int kPairStages = (kStages * kStageBytes) / kPairStageBytes;
 };
 
 struct ConvKParams {
@@ -56,18 +59,22 @@ struct ConvKParams {
   float* stats_partial;  // [gridDim.x][3][Cout]: per-CTA (sum, sum of squares, count) per output channel
 };
 
-// kCluster: CTAs run as clusters of two that work on two neighbouring pixel tiles of the SAME channel block; each CTA
-// loads half of the weight tile and TMA-multicasts it into both CTAs' shared memory, so the weight operand crosses
-// L2->SM once per pair (per-CTA operand traffic per K block: 16 KB + 16 KB instead of 16 KB + 32 KB at BLOCK_N=256).
-// The two CTAs stay in lock-step per smem stage: a stage is refilled only after BOTH MMA warps released it
-// (tcgen05.commit multicast onto both CTAs' empty barriers).
+// kCluster (CTA pair, tcgen05 cta_group::2): two CTAs of a cluster own two neighbouring pixel tiles of the SAME channel
+// block and execute ONE M=256 x N=BLOCK_N MMA per K step, issued by the leader CTA. Each CTA stages only its own 128
+// pixel rows of A and HALF of the weight rows (the tensor core reads the other half from the peer's shared memory), so
+// the operand bytes that cross L2->SM per FLOP drop by a third (16 KB + 16 KB instead of 16 KB + 32 KB per K block at
+// BLOCK_N=256) and the freed smem buys more pipeline stages. TMA completions of both CTAs are credited to the leader's
+// full barrier; the leader's tcgen05.commit is multicast to both CTAs' empty / tmem_full barriers; the peer's epilogue
+// hands its accumulator stage back by arriving on the leader's tmem_empty barrier.
 template <int BLOCK_N, bool kCluster>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
-  constexpr int kStages = Cfg::kStages;
+  constexpr int kStages = kCluster ? Cfg::kPairStages : Cfg::kStages;
+  constexpr int kStageBytes = kCluster ? Cfg::kPairStageBytes : Cfg::kStageBytes;
   const uint32_t cta_rank = kCluster ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
   // Work items: (pixel tile, channel tile) or, clustered, (pair of pixel tiles, channel tile) per cluster.
   const int item_first = kCluster ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int item_step = kCluster ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -83,11 +90,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint8_t* out_stage = smem + kStages * Cfg::kStageBytes;  // 2 x 16 KB
+  uint8_t* out_stage = smem + Cfg::kStages * Cfg::kStageBytes;  // 2 x 16 KB (same offset in both modes)
   uint8_t* misc = out_stage + 2 * kStageOutBytes;
+  static_assert(kStages <= 16, "barrier area sized for <= 16 stages");
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* empty_bar = full_bar + 16;
+  uint64_t* tmem_full = empty_bar + 16;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint32_t* row_mask = tmem_ptr + 1;                                // [4] valid-row bits per 32-row group
@@ -97,7 +105,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int num_kb = p.taps * p.k_chunks;
   const uint32_t a_bytes = static_cast<uint32_t>(p.bh * p.bw) * 128u;
-  const uint32_t stage_tx = a_bytes + static_cast<uint32_t>(Cfg::kBTileBytes);
+  // bytes credited to a full barrier per stage: own A + whole B, or (pair mode, leader's barrier) both A tiles + both B halves
+  const uint32_t stage_tx = (kCluster ? 2u * a_bytes : a_bytes) + static_cast<uint32_t>(Cfg::kBTileBytes);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -105,16 +114,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmC);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], kCluster ? 2 : 1);
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiThreads);
+      mbar_init(&tmem_empty[i], kCluster ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    if (kCluster) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_ptr);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
   }
   if (p.stats_partial != nullptr) {
     float* row = p.stats_partial + static_cast<size_t>(blockIdx.x) * 3 * p.Cout;
@@ -145,18 +155,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&empty_bar[s], par ^ 1);
           const int cb = kb / p.taps;
           const int t = kb - cb * p.taps;
-          uint8_t* a_dst = stage_base + s * Cfg::kStageBytes;
+          uint8_t* a_dst = stage_base + s * kStageBytes;
           uint8_t* b_dst = a_dst + kATileBytes;
-          mbar_expect_tx(&full_bar[s], stage_tx);
-          tma_load_4d(a_dst, &tmA, &full_bar[s], cb * kBlockK, w0 + p.dw[t], h0 + p.dh[t],
-                      img * p.img_mul + p.img_add[t]);
-          // 3-D weights [taps][rows][cols]: coordinates (k, row, tap)
           if (kCluster) {
-            // my half of the weight rows, multicast into both CTAs (each CTA's full barrier expects the whole tile)
-            constexpr int kHalfRows = BLOCK_N / 2;
-            tma_load_3d_mcast(b_dst + cta_rank * (Cfg::kBTileBytes / 2), &tmB, &full_bar[s], cb * kBlockK,
-                              n0 + static_cast<int>(cta_rank) * kHalfRows, p.wtap[t], static_cast<uint16_t>(3));
+            // both CTAs' loads complete on the LEADER's full barrier; only the leader arms it
+            const uint32_t lead_bar = mapa_u32(&full_bar[s], 0);
+            if (is_leader) mbar_expect_tx(&full_bar[s], stage_tx);
+            tma_load_4d_2sm(a_dst, &tmA, lead_bar, cb * kBlockK, w0 + p.dw[t], h0 + p.dh[t],
+                            img * p.img_mul + p.img_add[t]);
+            tma_load_3d_2sm(b_dst, &tmB, lead_bar, cb * kBlockK, n0 + static_cast<int>(cta_rank) * (BLOCK_N / 2),
+                            p.wtap[t]);
           } else {
+            mbar_expect_tx(&full_bar[s], stage_tx);
+            tma_load_4d(a_dst, &tmA, &full_bar[s], cb * kBlockK, w0 + p.dw[t], h0 + p.dh[t],
+                        img * p.img_mul + p.img_add[t]);
+            // 3-D weights [taps][rows][cols]: coordinates (k, row, tap)
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
                 "%5}], [%2];" ::"r"(smem_u32(b_dst)),
@@ -168,9 +181,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    // ===================================================================== MMA issuer (pair mode: leader CTA only)
+    if ((!kCluster || is_leader) && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(kCluster ? 2 * kBlockM : kBlockM, BLOCK_N, 0, 0);
       int it = 0;
       int tile_iter = 0;
       for (int item = item_first; item < num_items; item += item_step, ++tile_iter) {
@@ -184,21 +197,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t par = (it / kStages) & 1;
           mbar_wait(&full_bar[s], par);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(stage_base + s * Cfg::kStageBytes);
+          const uint32_t a_addr = smem_u32(stage_base + s * kStageBytes);
           const uint32_t b_addr = a_addr + kATileBytes;
           const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(b_addr, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle span
-            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            if (kCluster)
+              umma_bf16_2sm(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
           }
           // frees the smem stage once these MMAs have read it (clustered: in both CTAs, the peer multicasts into it)
-          if (kCluster) umma_commit_mcast(&empty_bar[s], static_cast<uint16_t>(3));
+          if (kCluster) umma_commit_2sm_mcast(&empty_bar[s], static_cast<uint16_t>(3));
           else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete
+        // accumulator complete (pair mode: each CTA's epilogue waits on its own tmem_full barrier)
+        if (kCluster) umma_commit_2sm_mcast(&tmem_full[as], static_cast<uint16_t>(3));
+        else umma_commit(&tmem_full[as]);
       }
     }
   } else {
@@ -216,7 +235,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&tmem_full[as_], (tile_iter >> 1) & 1);
         tc_fence_after();
         tc_fence_before();
-        mbar_arrive(&tmem_empty[as_]);
+        if (kCluster) mbar_arrive_cluster(mapa_u32(&tmem_empty[as_], 0));
+        else mbar_arrive(&tmem_empty[as_]);
         continue;
       }
       const int tiles_per_img = p.tiles_h * p.tiles_w;
@@ -396,9 +416,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         store_buf ^= 1;
       }
-      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      // all TMEM reads of this accumulator stage are done -> hand it back to the (leader's) MMA warp
       tc_fence_before();
-      mbar_arrive(&tmem_empty[as]);
+      if (kCluster) mbar_arrive_cluster(mapa_u32(&tmem_empty[as], 0));
+      else mbar_arrive(&tmem_empty[as]);
     }
     if (et == 0) tma_store_wait_all<0>();
   }
@@ -408,7 +429,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (kCluster) cluster_sync_all();  // the peer may still signal my barriers until it is done as well
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (kCluster) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 

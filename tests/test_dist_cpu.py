@@ -53,3 +53,26 @@ def test_syncbn_stats_exchange_and_timing_reduce_world2():
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_peer_exchange_slot_sequence_and_nccl_override(monkeypatch):
+    """Host logic of the NVLink peer exchange: (slot, seq) advance identically on every rank and a slot is only
+    reused with a strictly larger sequence number; SEMSEG_B200_SYNCBN=nccl disables the peer path."""
+    from semseg_b200 import p2p
+
+    class Fake(p2p.PeerExchange):
+        def __init__(self):
+            self.calls = 0
+    a, b = Fake(), Fake()
+    seen = {}
+    for _ in range(3 * p2p.N_SLOTS + 5):
+        sa, sb_ = a.next(), b.next()
+        assert sa == sb_
+        slot, seq = sa
+        assert 0 <= slot < p2p.N_SLOTS and seq >= 1
+        assert seq > seen.get(slot, 0)
+        seen[slot] = seq
+    assert p2p.SLOT_FLOATS >= 3 * 2048          # widest BatchNorm on the path (layer4 / PSA proj: 2048 channels)
+    monkeypatch.setenv("SEMSEG_B200_SYNCBN", "nccl")
+    assert p2p.get_exchange(object()) is None
+    assert p2p.exchange_kind() == "none"        # no process group initialised in this process
