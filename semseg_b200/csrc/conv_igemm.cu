@@ -438,7 +438,7 @@ static bool cluster_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SEMSEG_B200_CLUSTER");
-    v = (e && e[0] == '1') ? 1 : 0;  // opt-in until validated on hardware
+    v = (e && e[0] == '0') ? 0 : 1;  // CTA-pair mode by default (validated on B200); SEMSEG_B200_CLUSTER=0 disables
   }
   return v != 0;
 }
