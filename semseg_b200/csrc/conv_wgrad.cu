@@ -30,40 +30,54 @@ struct WgCfg {
   static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+  // CTA-pair mode (cta_group::2, M = 256 output channels over two CTAs): each CTA stages its own 128 dy channels and
+  // half of the x channels of the tile.
+  static constexpr int kPairBBoxes = BN / 128;
+  static constexpr int kPairStageBytes = (kWgABoxes + kPairBBoxes) * kWgBoxBytes;
+  static constexpr int kPairStages = (kStages * kStageBytes) / kPairStageBytes;
 };
 
 struct WgradKParams {
   int N, H, W, Cin, Cout, taps;
   int bh, bw, tiles_h, tiles_w, num_boxes;
-  int co_tiles, ci_tiles, n_splits, boxes_per_split, block_n;
+  int co_tiles, ci_tiles, n_splits, boxes_per_split, block_n, pair;
   int dh[SEMSEG_MAX_TAPS], dw[SEMSEG_MAX_TAPS], img_add[SEMSEG_MAX_TAPS];
   int img_mul;
   float* out;  // [n_splits][taps][Cout][Cin]
 };
 
-template <int kWgBlockN>
+// kPair: two CTAs of a cluster compute one 256(co) x BN(ci) tile with cta_group::2 MMAs (see conv_igemm.cu): the
+// leader issues the MMAs, both CTAs' TMA loads complete on the leader's full barrier, commits are multicast.
+template <int kWgBlockN, bool kPair>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                   const WgradKParams p) {
-  constexpr int kWgBBoxes = WgCfg<kWgBlockN>::kBBoxes;
-  constexpr int kWgStageBytes = WgCfg<kWgBlockN>::kStageBytes;
-  constexpr int kWgStages = WgCfg<kWgBlockN>::kStages;
+  constexpr int kWgBBoxes = kPair ? WgCfg<kWgBlockN>::kPairBBoxes : WgCfg<kWgBlockN>::kBBoxes;
+  constexpr int kWgStageBytes = kPair ? WgCfg<kWgBlockN>::kPairStageBytes : WgCfg<kWgBlockN>::kStageBytes;
+  constexpr int kWgStages = kPair ? WgCfg<kWgBlockN>::kPairStages : WgCfg<kWgBlockN>::kStages;
   constexpr int kWgTmemCols = WgCfg<kWgBlockN>::kTmemCols;
+  static_assert(kWgStages <= 16, "barrier area sized for <= 16 stages");
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* misc = smem + kWgStages * kWgStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);
-  uint64_t* empty_bar = full_bar + kWgStages;
-  uint64_t* tmem_full = empty_bar + kWgStages;
+  uint64_t* empty_bar = full_bar + 16;
+  uint64_t* tmem_full = empty_bar + 16;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // pair mode: p.co_tiles counts 256-channel tiles (one per cluster); this CTA owns the 128-channel half `cta_rank`
   const int units_per_split = p.taps * p.co_tiles * p.ci_tiles;
   const int num_units = units_per_split * p.n_splits;
+  const int unit_first = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const uint32_t box_bytes = static_cast<uint32_t>(p.bh * p.bw) * 128u;
-  const uint32_t stage_tx = box_bytes * (kWgABoxes + kWgBBoxes);
+  // bytes credited to a full barrier per stage (pair: both CTAs' loads land on the leader's barrier)
+  const uint32_t stage_tx = box_bytes * (kWgABoxes + kWgBBoxes) * (kPair ? 2u : 1u);
 
   // Zero all operand stages once: rows beyond the pixel box stay zero for the whole kernel.
   {
@@ -82,13 +96,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kWgEpiThreads);
+      mbar_init(&tmem_empty[i], kPair ? 2 * kWgEpiThreads : kWgEpiThreads);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kWgTmemCols>(tmem_ptr);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_2sm<kWgTmemCols>(tmem_ptr);
+    else tmem_alloc<kWgTmemCols>(tmem_ptr);
+  }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -97,6 +115,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     ci_t = unit % p.ci_tiles;
     int r = unit / p.ci_tiles;
     co_t = r % p.co_tiles;
+    if (kPair) co_t = 2 * co_t + static_cast<int>(cta_rank);  // my 128-channel half of the 256-channel tile
     r /= p.co_tiles;
     tap = r % p.taps;
     split = r / p.taps;
@@ -105,7 +124,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   if (warp == 0) {
     if (elect_one()) {
       int it = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      for (int unit = unit_first; unit < num_units; unit += unit_step) {
         int split, tap, co_t, ci_t;
         decode(unit, split, tap, co_t, ci_t);
         const int b0 = split * p.boxes_per_split;
@@ -120,23 +139,36 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           const int h0 = (rem / p.tiles_w) * p.bh;
           const int w0 = (rem % p.tiles_w) * p.bw;
           uint8_t* st = smem + s * kWgStageBytes;
-          mbar_expect_tx(&full_bar[s], stage_tx);
+          if (kPair) {
+            const uint32_t lead_bar = mapa_u32(&full_bar[s], 0);
+            if (is_leader) mbar_expect_tx(&full_bar[s], stage_tx);
 #pragma unroll
-          for (int i = 0; i < kWgABoxes; ++i)
-            tma_load_4d(st + i * kWgBoxBytes, &tmDY, &full_bar[s], co_t * 128 + i * 64, w0, h0, img);
+            for (int i = 0; i < kWgABoxes; ++i)
+              tma_load_4d_2sm(st + i * kWgBoxBytes, &tmDY, lead_bar, co_t * 128 + i * 64, w0, h0, img);
 #pragma unroll
-          for (int i = 0; i < kWgBBoxes; ++i)
-            tma_load_4d(st + (kWgABoxes + i) * kWgBoxBytes, &tmX, &full_bar[s], ci_t * kWgBlockN + i * 64,
-                        w0 + p.dw[tap], h0 + p.dh[tap], img * p.img_mul + p.img_add[tap]);
+            for (int i = 0; i < kWgBBoxes; ++i)
+              tma_load_4d_2sm(st + (kWgABoxes + i) * kWgBoxBytes, &tmX, lead_bar,
+                              ci_t * kWgBlockN + static_cast<int>(cta_rank) * (kWgBlockN / 2) + i * 64,
+                              w0 + p.dw[tap], h0 + p.dh[tap], img * p.img_mul + p.img_add[tap]);
+          } else {
+            mbar_expect_tx(&full_bar[s], stage_tx);
+#pragma unroll
+            for (int i = 0; i < kWgABoxes; ++i)
+              tma_load_4d(st + i * kWgBoxBytes, &tmDY, &full_bar[s], co_t * 128 + i * 64, w0, h0, img);
+#pragma unroll
+            for (int i = 0; i < kWgBBoxes; ++i)
+              tma_load_4d(st + (kWgABoxes + i) * kWgBoxBytes, &tmX, &full_bar[s], ci_t * kWgBlockN + i * 64,
+                          w0 + p.dw[tap], h0 + p.dh[tap], img * p.img_mul + p.img_add[tap]);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, kWgBlockN, 1, 1);  // A and B MN-major
+    if ((!kPair || is_leader) && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(kPair ? 256 : 128, kWgBlockN, 1, 1);  // A and B MN-major
       int it = 0;
       int unit_iter = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++unit_iter) {
+      for (int unit = unit_first; unit < num_units; unit += unit_step, ++unit_iter) {
         int split, tap, co_t, ci_t;
         decode(unit, split, tap, co_t, ci_t);
         const int b0 = split * p.boxes_per_split;
@@ -159,19 +191,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 #pragma unroll
           for (int k = 0; k < kWgBoxPixels / 16; ++k) {
             // 16 pixels along K = 2048 bytes -> +128 in 16-byte units
-            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 128), bdesc + static_cast<uint64_t>(k * 128), idesc,
-                      (b > b0 || k > 0) ? 1u : 0u);
+            if (kPair)
+              umma_bf16_2sm(d_tmem, adesc + static_cast<uint64_t>(k * 128), bdesc + static_cast<uint64_t>(k * 128),
+                            idesc, (b > b0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 128), bdesc + static_cast<uint64_t>(k * 128), idesc,
+                        (b > b0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          if (kPair) umma_commit_2sm_mcast(&empty_bar[s], static_cast<uint16_t>(3));
+          else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tmem_full[as]);
+        if (kPair) umma_commit_2sm_mcast(&tmem_full[as], static_cast<uint16_t>(3));
+        else umma_commit(&tmem_full[as]);
       }
     }
   } else {
     const int g = warp & 3;
     const int row = g * 32 + lane;  // Cout index within the tile
     int unit_iter = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++unit_iter) {
+    for (int unit = unit_first; unit < num_units; unit += unit_step, ++unit_iter) {
       int split, tap, co_t, ci_t;
       decode(unit, split, tap, co_t, ci_t);
       const int as = unit_iter & 1;
@@ -205,15 +243,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[as]);
+      if (kPair) mbar_arrive_cluster(mapa_u32(&tmem_empty[as], 0));
+      else mbar_arrive(&tmem_empty[as]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<kWgTmemCols>(tmem_base);
+    if (kPair) tmem_dealloc_2sm<kWgTmemCols>(tmem_base);
+    else tmem_dealloc<kWgTmemCols>(tmem_base);
   }
 }
 
@@ -231,16 +272,41 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int n_splits
   }
 }
 
-template <int BN>
+static bool wgrad_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEMSEG_B200_CLUSTER");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <int BN, bool kPair>
 static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradKParams& kp, int grid,
                         cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  WgCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  conv_wgrad_kernel<BN><<<grid, kWgThreads, WgCfg<BN>::kSmemBytes, stream>>>(tmDY, tmX, kp);
+  if (!kPair) {
+    conv_wgrad_kernel<BN, false><<<grid, kWgThreads, WgCfg<BN>::kSmemBytes, stream>>>(tmDY, tmX, kp);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = WgCfg<BN>::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SB_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN, true>, tmDY, tmX, kp));
+  }
   return SEMSEG_OK;
 }
 
@@ -253,11 +319,14 @@ static void wgrad_geometry(const semseg_wgrad_desc* d, WgradKParams* kp) {
   kp->co_tiles = cdiv(d->Cout, 128);
   kp->block_n = d->Cin > 128 ? 256 : (d->Cin > 64 ? 128 : 64);
   kp->ci_tiles = cdiv(d->Cin, kp->block_n);
+  // CTA-pair mode needs two 128-channel dy tiles per cluster and a >= 128-channel x tile to halve
+  kp->pair = (wgrad_pair_enabled() && d->Cout > 128 && kp->block_n >= 128) ? 1 : 0;
+  if (kp->pair) kp->co_tiles = cdiv(d->Cout, 256);
   const int units = d->taps * kp->co_tiles * kp->ci_tiles;
   int splits = d->n_splits;
   if (splits <= 0) {
     // aim for >= 2 waves of work units over the SMs, but keep >= 16 K-blocks per unit
-    const int target = 2 * num_sms();
+    const int target = 2 * num_sms() / (kp->pair ? 2 : 1);
     splits = cdiv(target, units);
     const int max_by_k = kp->num_boxes / 16 > 0 ? kp->num_boxes / 16 : 1;
     if (splits > max_by_k) splits = max_by_k;
@@ -315,12 +384,19 @@ extern "C" int semseg_conv_wgrad(const semseg_wgrad_desc* d, void* stream_) {
     if (r) return r;
   }
   const int units = kp.taps * kp.co_tiles * kp.ci_tiles * kp.n_splits;
-  const int grid = units < num_sms() ? units : num_sms();
   int rc = SEMSEG_OK;
-  switch (kp.block_n) {
-    case 256: rc = launch_wgrad<256>(tmDY, tmX, kp, grid, stream); break;
-    case 128: rc = launch_wgrad<128>(tmDY, tmX, kp, grid, stream); break;
-    default: rc = launch_wgrad<64>(tmDY, tmX, kp, grid, stream); break;
+  if (kp.pair) {
+    const int max_clusters = num_sms() / 2;
+    const int grid = 2 * (units < max_clusters ? units : max_clusters);
+    rc = kp.block_n == 256 ? launch_wgrad<256, true>(tmDY, tmX, kp, grid, stream)
+                           : launch_wgrad<128, true>(tmDY, tmX, kp, grid, stream);
+  } else {
+    const int grid = units < num_sms() ? units : num_sms();
+    switch (kp.block_n) {
+      case 256: rc = launch_wgrad<256, false>(tmDY, tmX, kp, grid, stream); break;
+      case 128: rc = launch_wgrad<128, false>(tmDY, tmX, kp, grid, stream); break;
+      default: rc = launch_wgrad<64, false>(tmDY, tmX, kp, grid, stream); break;
+    }
   }
   if (rc) return rc;
   SB_LAUNCHED();
