@@ -95,12 +95,12 @@ typedef struct semseg_conv_desc {
   int32_t res_pitch;
   float* out_f32; /* F32 mode output */
   int32_t out_pitch;
-  /* RAW mode statistics: stats_partial [rows][3][Cout] = per-CTA (sum, sum of squares, count) of the stored bf16
-   * outputs per channel, rows = semseg_conv_stats_rows(); NULL to skip. The kernel zeroes and fills every row. */
+  /* RAW mode statistics: stats_partial [rows][3][Cout] = per epilogue-warp (sum, sum of squares, count) of the stored
+   * bf16 outputs per channel, rows = semseg_conv_stats_rows(); NULL to skip. The kernel zeroes and fills every row. */
   float* stats_partial;
 } semseg_conv_desc;
 
-/* Rows of the statistics buffer (= CTAs launched) for an [N,H,W] x Cout output. */
+/* Rows of the statistics buffer (= 4 x CTAs launched) for an [N,H,W] x Cout output. */
 int semseg_conv_stats_rows(int N, int H, int W, int Cout);
 int semseg_conv_fprop(const semseg_conv_desc* d, void* stream);
 

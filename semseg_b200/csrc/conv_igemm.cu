@@ -56,7 +56,7 @@ struct ConvKParams {
   int res_pitch;
   float* out_f32;
   int out_pitch;
-  float* stats_partial;  // [gridDim.x][3][Cout]: per-CTA (sum, sum of squares, count) per output channel
+  float* stats_partial;  // [gridDim.x * 4][3][Cout]: per epilogue warp (sum, sum of squares, count) per channel
 };
 
 // kCluster (CTA pair, tcgen05 cta_group::2): two CTAs of a cluster own two neighbouring pixel tiles of the SAME channel
@@ -98,8 +98,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = empty_bar + 16;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint32_t* row_mask = tmem_ptr + 1;                                // [4] valid-row bits per 32-row group
-  float* stat_scratch = reinterpret_cast<float*>(misc + 512);       // [3 row quarters][32 column pairs][4] = 1536 B
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,9 +124,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (kCluster) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_ptr);
     else tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
   }
-  if (p.stats_partial != nullptr) {
-    float* row = p.stats_partial + static_cast<size_t>(blockIdx.x) * 3 * p.Cout;
-    for (int i = threadIdx.x; i < 3 * p.Cout; i += kNumThreads) row[i] = 0.f;
+  if (p.stats_partial != nullptr) {  // four statistics rows per CTA: one per epilogue warp (32 accumulator rows each)
+    float* row = p.stats_partial + static_cast<size_t>(blockIdx.x) * 4 * 3 * p.Cout;
+    for (int i = threadIdx.x; i < 4 * 3 * p.Cout; i += kNumThreads) row[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -249,10 +247,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int wi = row - hi * p.bw;
       const bool row_valid = (row < p.bh * p.bw) && (h0 + hi < p.H) && (w0 + wi < p.W);
       const long long pix = (static_cast<long long>(img) * p.H + (h0 + hi)) * p.W + (w0 + wi);
-      {
-        const uint32_t m = __ballot_sync(0xffffffffu, row_valid);
-        if (lane == 0) row_mask[g] = m;
-      }
+      const uint32_t row_msk = __ballot_sync(0xffffffffu, row_valid);  // valid rows of this warp's 32-row group
       const int as = tile_iter & 1;
       const uint32_t apar = (tile_iter >> 1) & 1;
       mbar_wait(&tmem_full[as], apar);
@@ -268,8 +263,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool do_stats = p.stats_partial != nullptr && p.epi_mode == SEMSEG_EPI_RAW;
         float st_old[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float* st_dst = nullptr;
-        if (do_stats && et < 32) {
-          st_dst = p.stats_partial + static_cast<size_t>(blockIdx.x) * 3 * p.Cout + c0 + 2 * et;
+        if (do_stats) {  // every epilogue warp owns statistics row (blockIdx.x*4 + g); lane = column pair
+          st_dst = p.stats_partial + (static_cast<size_t>(blockIdx.x) * 4 + g) * 3 * p.Cout + c0 + 2 * lane;
           st_old[0] = st_dst[0];
           st_old[1] = st_dst[1];
           st_old[2] = st_dst[p.Cout];
@@ -352,67 +347,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           *reinterpret_cast<uint4*>(obuf + row * 128 + ((j8 ^ (row & 7)) << 4)) = o;
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, kEpiThreads);
-        if (et == 0) {
-          tma_store_4d(&tmC, obuf, c0, w0, h0, img);
-          tma_store_commit();
-        }
-
         if (do_stats) {
-          // Per-column statistics of the bf16 values just staged (exactly what BN-apply will read back).
-          // Thread -> column pair cp (2 adjacent bf16 = one 4-byte word, conflict-free across the warp) and a
-          // quarter of the rows; one pass accumulates sum and sum of squares, the four quarters are combined in
-          // a fixed order and converted to (sum, M2 about the tile mean).
-          const int cp = et & 31;
-          const int rq = et >> 5;
-          const uint32_t msk = row_mask[rq];
+          // Per-column statistics of the bf16 values just staged (exactly what BN-apply will read back). Each warp
+          // reduces the 32 rows it wrote itself (only a __syncwarp away), lane = column pair (one 4-byte word,
+          // conflict-free), one pass of sum and sum of squares, then a read-modify-write of the warp's own running
+          // (sum, sum of squares, count) row in global memory: no cross-warp traffic, fixed order -> deterministic.
+          __syncwarp();
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          const uint8_t* base = obuf + (cp & 3) * 4;
-          const int chunk16 = cp >> 2;
+          const uint8_t* base = obuf + (lane & 3) * 4;
+          const int chunk16 = lane >> 2;
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
-            const int rr = rq * 32 + r;
-            if ((msk >> r) & 1u) {
-              const __nv_bfloat162 v =
+            const int rr = g * 32 + r;
+            if ((row_msk >> r) & 1u) {
+              const __nv_bfloat162 bv =
                   *reinterpret_cast<const __nv_bfloat162*>(base + rr * 128 + ((chunk16 ^ (rr & 7)) << 4));
-              const float2 f = __bfloat1622float2(v);
+              const float2 f = __bfloat1622float2(bv);
               s0 += f.x;
               s1 += f.y;
               q0 = fmaf(f.x, f.x, q0);
               q1 = fmaf(f.y, f.y, q1);
             }
           }
-          if (rq > 0) {  // quarters 1..3 publish to scratch ([3][32][4] floats = 1536 B); quarter 0 combines
-            float* sc = stat_scratch + ((rq - 1) * 32 + cp) * 4;
-            sc[0] = s0;
-            sc[1] = s1;
-            sc[2] = q0;
-            sc[3] = q1;
-          }
-          named_bar_sync(2, kEpiThreads);
-          if (rq == 0) {
-            float S0 = s0, S1 = s1, Q0 = q0, Q1 = q1;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const float* o = stat_scratch + (k * 32 + cp) * 4;
-              S0 += o[0];
-              S1 += o[1];
-              Q0 += o[2];
-              Q1 += o[3];
-            }
-            const float nt = static_cast<float>(__popc(row_mask[0]) + __popc(row_mask[1]) + __popc(row_mask[2]) +
-                                                __popc(row_mask[3]));
-            // Per-CTA running (sum, sum of squares, count) per column: this CTA is the only writer of its row and
-            // a given column is always handled by the same thread, so plain read-modify-write is race free and
-            // the accumulation order (this CTA's tile sequence) is fixed -> deterministic.
-            st_dst[0] = st_old[0] + S0;
-            st_dst[1] = st_old[1] + S1;
-            st_dst[p.Cout] = st_old[2] + Q0;
-            st_dst[p.Cout + 1] = st_old[3] + Q1;
-            st_dst[2 * p.Cout] = st_old[4] + nt;
-            st_dst[2 * p.Cout + 1] = st_old[5] + nt;
-          }
-          named_bar_sync(2, kEpiThreads);  // scratch may be rewritten by the next chunk
+          const float nt = static_cast<float>(__popc(row_msk));
+          st_dst[0] = st_old[0] + s0;
+          st_dst[1] = st_old[1] + s1;
+          st_dst[p.Cout] = st_old[2] + q0;
+          st_dst[p.Cout + 1] = st_old[3] + q1;
+          st_dst[2 * p.Cout] = st_old[4] + nt;
+          st_dst[2 * p.Cout + 1] = st_old[5] + nt;
+        }
+        named_bar_sync(1, kEpiThreads);
+        if (et == 0) {
+          tma_store_4d(&tmC, obuf, c0, w0, h0, img);
+          tma_store_commit();
         }
         store_buf ^= 1;
       }
@@ -502,8 +470,8 @@ extern "C" int semseg_conv_stats_rows(int N, int H, int W, int Cout) {
   if (N <= 0 || H <= 0 || W <= 0 || Cout <= 0) return SEMSEG_E_INVALID;
   int bh, bw;
   sb::choose_box(H, W, sb::kBlockM, &bh, &bw);
-  bool clustered;
-  return sb::conv_grid(N * sb::cdiv(H, bh) * sb::cdiv(W, bw), sb::cdiv(Cout, conv_block_n(Cout)), &clustered);
+  bool clustered;  // four statistics rows per CTA (one per epilogue warp)
+  return 4 * sb::conv_grid(N * sb::cdiv(H, bh) * sb::cdiv(W, bw), sb::cdiv(Cout, conv_block_n(Cout)), &clustered);
 }
 
 extern "C" int semseg_conv_fprop(const semseg_conv_desc* d, void* stream_) {

@@ -70,4 +70,4 @@ def test_invalid_arguments_return_error_codes_without_gpu():
     assert b"odd" in lib.semseg_last_error()
     d = _lib.ConvDesc()
     assert lib.semseg_conv_fprop(ctypes.byref(d), None) == -1
-    assert lib.semseg_conv_stats_rows(1, 8, 16, 64) == 1
+    assert lib.semseg_conv_stats_rows(1, 8, 16, 64) == 4
