@@ -74,9 +74,23 @@ __global__ void bn_merge_conv_partials_kernel(const float* __restrict__ part, in
   const int cl = threadIdx.x & 31;
   const int tl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
+  // each lane adds the raw (sum, sum of squares, count) of its rows (no divisions), converts once to moments;
+  // the 32 lanes are then merged with Chan's formula in a fixed order
   Moments acc = {0.f, 0.f, 0.f};
-  if (c < C)
-    for (int t = tl; t < T; t += 32) acc = merge(acc, conv_row_moments(part, t, C, c));
+  if (c < C) {
+    float S = 0.f, Q = 0.f, n = 0.f;
+    for (int t = tl; t < T; t += 32) {
+      const float* row = part + static_cast<size_t>(t) * 3 * C;
+      S += row[c];
+      Q += row[C + c];
+      n += row[2 * C + c];
+    }
+    if (n > 0.f) {
+      acc.n = n;
+      acc.mean = S / n;
+      acc.m2 = fmaxf(Q - S * acc.mean, 0.f);
+    }
+  }
   sm[tl][cl] = acc;
   __syncthreads();
   if (tl == 0 && c < C) {
@@ -99,9 +113,23 @@ __global__ void bn_finalize_partials_kernel(const float* __restrict__ part, int 
   const int cl = threadIdx.x & 31;
   const int tl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
+  // each lane adds the raw (sum, sum of squares, count) of its rows (no divisions), converts once to moments;
+  // the 32 lanes are then merged with Chan's formula in a fixed order
   Moments acc = {0.f, 0.f, 0.f};
-  if (c < C)
-    for (int t = tl; t < T; t += 32) acc = merge(acc, conv_row_moments(part, t, C, c));
+  if (c < C) {
+    float S = 0.f, Q = 0.f, n = 0.f;
+    for (int t = tl; t < T; t += 32) {
+      const float* row = part + static_cast<size_t>(t) * 3 * C;
+      S += row[c];
+      Q += row[C + c];
+      n += row[2 * C + c];
+    }
+    if (n > 0.f) {
+      acc.n = n;
+      acc.mean = S / n;
+      acc.m2 = fmaxf(Q - S * acc.mean, 0.f);
+    }
+  }
   sm[tl][cl] = acc;
   __syncthreads();
   if (tl == 0 && c < C) {
@@ -626,9 +654,23 @@ __global__ void bn_finalize_p2p_kernel(const float* __restrict__ part, int T, in
   const int cl = threadIdx.x & 31;
   const int tl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
+  // each lane adds the raw (sum, sum of squares, count) of its rows (no divisions), converts once to moments;
+  // the 32 lanes are then merged with Chan's formula in a fixed order
   Moments acc = {0.f, 0.f, 0.f};
-  if (c < C)
-    for (int t = tl; t < T; t += 32) acc = merge(acc, conv_row_moments(part, t, C, c));
+  if (c < C) {
+    float S = 0.f, Q = 0.f, n = 0.f;
+    for (int t = tl; t < T; t += 32) {
+      const float* row = part + static_cast<size_t>(t) * 3 * C;
+      S += row[c];
+      Q += row[C + c];
+      n += row[2 * C + c];
+    }
+    if (n > 0.f) {
+      acc.n = n;
+      acc.mean = S / n;
+      acc.m2 = fmaxf(Q - S * acc.mean, 0.f);
+    }
+  }
   sm[tl][cl] = acc;
   __syncthreads();
   const size_t off = static_cast<size_t>(pa.slot) * pa.slot_floats;
