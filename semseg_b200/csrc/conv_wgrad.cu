@@ -41,6 +41,9 @@ struct WgradKParams {
   int N, H, W, Cin, Cout, taps;
   int bh, bw, tiles_h, tiles_w, num_boxes;
   int co_tiles, ci_tiles, n_splits, boxes_per_split, block_n, pair;
+  // Multi-tap units for narrow inputs (Cin <= 128, 3x3): the 256-wide N tile holds `tu` taps x (cin_boxes*64) channels,
+  // so the dy tile is loaded once for `tu` taps instead of once per tap (the narrow layers are L2->SM bound).
+  int tu, cin_boxes, unit_taps, oob_img;
   int dh[SEMSEG_MAX_TAPS], dw[SEMSEG_MAX_TAPS], img_add[SEMSEG_MAX_TAPS];
   int img_mul;
   float* out;  // [n_splits][taps][Cout][Cin]
@@ -71,7 +74,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // pair mode: p.co_tiles counts 256-channel tiles (one per cluster); this CTA owns the 128-channel half `cta_rank`
-  const int units_per_split = p.taps * p.co_tiles * p.ci_tiles;
+  const int units_per_split = p.unit_taps * p.co_tiles * p.ci_tiles;
   const int num_units = units_per_split * p.n_splits;
   const int unit_first = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int unit_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -117,8 +120,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     co_t = r % p.co_tiles;
     if (kPair) co_t = 2 * co_t + static_cast<int>(cta_rank);  // my 128-channel half of the 256-channel tile
     r /= p.co_tiles;
-    tap = r % p.taps;
-    split = r / p.taps;
+    tap = r % p.unit_taps;   // tap, or tap group when p.tu > 1
+    split = r / p.unit_taps;
   };
 
   if (warp == 0) {
@@ -155,10 +158,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 #pragma unroll
             for (int i = 0; i < kWgABoxes; ++i)
               tma_load_4d(st + i * kWgBoxBytes, &tmDY, &full_bar[s], co_t * 128 + i * 64, w0, h0, img);
+            if (p.tu > 1) {
 #pragma unroll
-            for (int i = 0; i < kWgBBoxes; ++i)
-              tma_load_4d(st + (kWgABoxes + i) * kWgBoxBytes, &tmX, &full_bar[s], ci_t * kWgBlockN + i * 64,
-                          w0 + p.dw[tap], h0 + p.dh[tap], img * p.img_mul + p.img_add[tap]);
+              for (int i = 0; i < kWgBBoxes; ++i) {   // box i = (tap of the group, 64-channel block)
+                const int ti = tap * p.tu + i / p.cin_boxes;
+                const bool live = ti < p.taps;        // dead taps of the last group: fully out-of-range box -> zeros
+                const int tt = live ? ti : 0;
+                tma_load_4d(st + (kWgABoxes + i) * kWgBoxBytes, &tmX, &full_bar[s], (i % p.cin_boxes) * 64,
+                            w0 + p.dw[tt], h0 + p.dh[tt], live ? img * p.img_mul + p.img_add[tt] : p.oob_img);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < kWgBBoxes; ++i)
+                tma_load_4d(st + (kWgABoxes + i) * kWgBoxBytes, &tmX, &full_bar[s], ci_t * kWgBlockN + i * 64,
+                            w0 + p.dw[tap], h0 + p.dh[tap], img * p.img_mul + p.img_add[tap]);
+            }
           }
         }
       }
@@ -218,27 +232,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       tc_fence_after();
       const int co = co_t * 128 + row;
       const int ci0 = ci_t * kWgBlockN;
-      float* orow = p.out + ((static_cast<size_t>(split) * p.taps + tap) * p.Cout + co) * p.Cin + ci0;
 #pragma unroll 1
       for (int ch = 0; ch < kWgBlockN / 32; ++ch) {
-        if (ci0 + ch * 32 >= p.Cin) break;
+        // destination of this 32-column block: (tap, first input channel)
+        int tap_o = tap, ci_o = ci0 + ch * 32;
+        if (p.tu > 1) {
+          const int box = ch >> 1;
+          tap_o = tap * p.tu + box / p.cin_boxes;
+          ci_o = (box % p.cin_boxes) * 64 + (ch & 1) * 32;
+          if (tap_o >= p.taps) continue;
+        }
+        if (ci_o >= p.Cin) {
+          if (p.tu > 1) continue;
+          break;
+        }
         uint32_t v[32];
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(g * 32) << 16) + static_cast<uint32_t>(as * kWgBlockN + ch * 32);
         tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
         if (co < p.Cout) {
-          if (ci0 + ch * 32 + 32 <= p.Cin && (p.Cin & 3) == 0) {
+          float* orow = p.out + ((static_cast<size_t>(split) * p.taps + tap_o) * p.Cout + co) * p.Cin + ci_o;
+          if (ci_o + 32 <= p.Cin && (p.Cin & 3) == 0) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               float4 f = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                      __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-              *reinterpret_cast<float4*>(orow + ch * 32 + 4 * q) = f;
+              *reinterpret_cast<float4*>(orow + 4 * q) = f;
             }
           } else {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
-              if (ci0 + ch * 32 + q < p.Cin) orow[ch * 32 + q] = __uint_as_float(v[q]);
+              if (ci_o + q < p.Cin) orow[q] = __uint_as_float(v[q]);
           }
         }
       }
@@ -322,7 +347,17 @@ static void wgrad_geometry(const semseg_wgrad_desc* d, WgradKParams* kp) {
   // CTA-pair mode needs two 128-channel dy tiles per cluster and a >= 128-channel x tile to halve
   kp->pair = (wgrad_pair_enabled() && d->Cout > 128 && kp->block_n >= 128) ? 1 : 0;
   if (kp->pair) kp->co_tiles = cdiv(d->Cout, 256);
-  const int units = d->taps * kp->co_tiles * kp->ci_tiles;
+  kp->tu = 1;
+  kp->cin_boxes = cdiv(d->Cin, 64);
+  kp->unit_taps = d->taps;
+  kp->oob_img = d->Nin;
+  if (!kp->pair && d->taps > 1 && d->Cin <= 128) {   // narrow 3x3: several taps share one dy tile (N tile = 256)
+    kp->tu = 4 / kp->cin_boxes;
+    kp->unit_taps = cdiv(d->taps, kp->tu);
+    kp->block_n = 256;
+    kp->ci_tiles = 1;
+  }
+  const int units = kp->unit_taps * kp->co_tiles * kp->ci_tiles;
   int splits = d->n_splits;
   if (splits <= 0) {
     // aim for >= 2 waves of work units over the SMs, but keep >= 16 K-blocks per unit
@@ -383,7 +418,7 @@ extern "C" int semseg_conv_wgrad(const semseg_wgrad_desc* d, void* stream_) {
     int r = encode_tmap_bf16(&tmX, d->x, 4, dims, str, box);
     if (r) return r;
   }
-  const int units = kp.taps * kp.co_tiles * kp.ci_tiles * kp.n_splits;
+  const int units = kp.unit_taps * kp.co_tiles * kp.ci_tiles * kp.n_splits;
   int rc = SEMSEG_OK;
   if (kp.pair) {
     const int max_clusters = num_sms() / 2;
