@@ -25,7 +25,7 @@ __device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
 // ------------------------------------------------------------------------------------------------
 // partials [T][2][C] (sum, M2 about the tile mean) + counts [T]  ->  out [3][C] (mean, M2, count)
 // block = 32 channels x 32 tile lanes.
-__global__ void bn_merge_partials_kernel(const float* __restrict__ part, const float* __restrict__ cnt, int T, int C,
+__global__ void __launch_bounds__(1024) bn_merge_partials_kernel(const float* __restrict__ part, const float* __restrict__ cnt, int T, int C,
                                          float* __restrict__ out) {
   __shared__ Moments sm[32][33];
   const int cl = threadIdx.x & 31;
@@ -69,7 +69,7 @@ __device__ __forceinline__ Moments conv_row_moments(const float* __restrict__ pa
   return m;
 }
 
-__global__ void bn_merge_conv_partials_kernel(const float* __restrict__ part, int T, int C, float* __restrict__ out) {
+__global__ void __launch_bounds__(1024) bn_merge_conv_partials_kernel(const float* __restrict__ part, int T, int C, float* __restrict__ out) {
   __shared__ Moments sm[32][33];
   const int cl = threadIdx.x & 31;
   const int tl = threadIdx.x >> 5;
@@ -104,7 +104,7 @@ __global__ void bn_merge_conv_partials_kernel(const float* __restrict__ part, in
 
 // ------------------------------------------------------------------------------------------------
 // Single-rank fast path: merge the per-tile partials AND finalise in one launch (no SyncBN exchange needed).
-__global__ void bn_finalize_partials_kernel(const float* __restrict__ part, int T, int C,
+__global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float* __restrict__ part, int T, int C,
                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                             float eps, float momentum, float* __restrict__ running_mean,
                                             float* __restrict__ running_var, float* __restrict__ mean_invstd,
@@ -444,7 +444,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
 }
 
 // stage 2: sums[2][C] = sum over chunks (fixed order).
-__global__ void bn_bwd_reduce_final_kernel(const float* __restrict__ part, int chunks, int C,
+__global__ void __launch_bounds__(1024) bn_bwd_reduce_final_kernel(const float* __restrict__ part, int chunks, int C,
                                            float* __restrict__ sums) {
   __shared__ float sm[32][33];
   const int cl = threadIdx.x & 31;
@@ -646,7 +646,7 @@ __device__ __forceinline__ void peer_publish_and_wait(const PeerArgs& pa) {
 }
 
 // Forward: merge this rank's conv partials, exchange (mean, M2, n), merge over ranks, finalise.
-__global__ void bn_finalize_p2p_kernel(const float* __restrict__ part, int T, int C, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(1024) bn_finalize_p2p_kernel(const float* __restrict__ part, int T, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, float momentum,
                                        float* __restrict__ running_mean, float* __restrict__ running_var,
                                        float* __restrict__ mean_invstd, float* __restrict__ scale_shift, PeerArgs pa) {
@@ -710,7 +710,7 @@ __global__ void bn_finalize_p2p_kernel(const float* __restrict__ part, int T, in
 
 // Backward: finish the local chunk reduction, exchange [sum dz, sum dz*xhat], add over ranks in rank order.
 //   sums_local [2][C] (feeds dgamma/dbeta, averaged later by DDP), sums_total [2][C] (feeds dx).
-__global__ void bn_bwd_reduce_final_p2p_kernel(const float* __restrict__ part, int chunks, int C,
+__global__ void __launch_bounds__(1024) bn_bwd_reduce_final_p2p_kernel(const float* __restrict__ part, int chunks, int C,
                                                float* __restrict__ sums_local, float* __restrict__ sums_total,
                                                PeerArgs pa) {
   __shared__ float sm[32][33];
