@@ -201,6 +201,48 @@ def test_bn_kernels_vs_torch():
     assert util.rel_l2(dgb[0], gm.grad) < 1e-5 and util.rel_l2(dgb[1], bt.grad) < 1e-5
 
 
+def test_peer_exchange_kernels_world_of_one():
+    """The NVLink SyncBN exchange kernels with a one-rank exchange (a local buffer stands in for the symmetric one):
+    same statistics as the single-GPU finalize / reduce, across more calls than there are slots (slot reuse)."""
+    import ctypes
+    from semseg_b200 import functional as SF, ops, p2p
+
+    class LocalExchange(p2p.PeerExchange):
+        def __init__(self):
+            self.world, self.rank, self.calls = 1, 0, 0
+            flag_words = p2p.N_SLOTS
+            self.buf = torch.zeros(flag_words + p2p.N_SLOTS * p2p.SLOT_FLOATS, device="cuda")
+            self.flag_ptrs = (ctypes.c_void_p * 1)(self.buf.data_ptr())
+            self.data_ptrs = (ctypes.c_void_p * 1)(self.buf.data_ptr() + 4 * flag_words)
+            self.counter = torch.zeros((1,), dtype=torch.int32, device="cuda")
+
+    px = LocalExchange()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for it, c in enumerate([64, 256, 2048, 96] * 3):
+        n, h, w = 2, 12, 11
+        x = (torch.randn((n, h, w, c), device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
+        gamma = torch.rand((c,), device="cuda", generator=g) + 0.5
+        beta = torch.randn((c,), device="cuda", generator=g)
+        conv = torch.nn.Conv2d(c, c, 1, bias=False).cuda()
+        y, sp = ops.conv_fprop(x, SF.packed(conv).wf, c, ops.conv_taps(1, 1), stats=True)
+        rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+        rm2, rv2 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+        mi_ref, ss_ref = ops.bn_finalize_partials(sp, gamma, beta, 1e-5, 0.1, rm2, rv2)
+        mi, ss = ops.bn_finalize_p2p(sp, gamma, beta, 1e-5, 0.1, rm, rv, px)
+        close = lambda a, b: torch.allclose(a, b, rtol=1e-5, atol=1e-6)     # noqa: E731
+        assert close(mi, mi_ref) and close(ss, ss_ref), (it, c)
+        assert close(rm, rm2) and close(rv, rv2)
+        dy = torch.randn((n, h, w, c), device="cuda", generator=g).to(torch.bfloat16)
+        sums_ref = ops.bn_bwd_reduce(dy, None, y, mi, True, scale_shift=ss)
+        loc, tot = ops.bn_bwd_reduce_p2p(dy, None, y, mi, True, ss, px)
+        assert close(loc, sums_ref) and close(tot, sums_ref), (it, c)
+    # slot reuse: wrap the slot ring twice with the last case
+    for _ in range(2 * p2p.N_SLOTS + 3):
+        mi, ss = ops.bn_finalize_p2p(sp, gamma, beta, 1e-5, 0.1, None, None, px)
+    torch.cuda.synchronize()
+    assert close(mi, mi_ref) and close(ss, ss_ref)
+
+
 # ------------------------------------------------------------------------------------------------ fused tail / PPM
 @pytest.mark.parametrize("shape", [(2, 9, 9, 150), (2, 60, 60, 150), (1, 90, 90, 19), (3, 17, 9, 21)])
 def test_upsample_ce_fused_vs_torch(shape):
