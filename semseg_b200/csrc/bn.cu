@@ -55,18 +55,32 @@ __global__ void __launch_bounds__(1024) bn_merge_partials_kernel(const float* __
   }
 }
 
-// Row of the conv epilogue's statistics buffer [rows][3][C] = (sum, sum of squares, count) -> Moments.
-__device__ __forceinline__ Moments conv_row_moments(const float* __restrict__ part, int t, int C, int c) {
-  Moments m = {0.f, 0.f, 0.f};
-  const float* row = part + static_cast<size_t>(t) * 3 * C;
-  const float n = row[2 * C + c];
-  if (n > 0.f) {
-    const float s = row[c], q = row[C + c];
-    m.n = n;
-    m.mean = s / n;
-    m.m2 = fmaxf(q - s * m.mean, 0.f);
+// The conv epilogue's statistics buffer is [rows][3][C] = (sum, sum of squares, count) per epilogue warp.
+
+// Adds the raw (sum, sum of squares, count) of rows tl, tl+32, ... for channel c. The rows are independent loads, so
+// eight rows (24 loads) are issued before the first add: the kernel is a chain of ~T/256 memory round trips instead
+// of T/32.
+__device__ __forceinline__ void accumulate_rows(const float* __restrict__ part, int T, int C, int c, int tl, float& S,
+                                                float& Q, float& n) {
+  constexpr int U = 8;
+  for (int t0 = tl; t0 < T; t0 += 32 * U) {
+    float s[U], q[U], m[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + 32 * u;
+      const bool ok = t < T;
+      const float* row = part + static_cast<size_t>(ok ? t : 0) * 3 * C;
+      s[u] = ok ? row[c] : 0.f;
+      q[u] = ok ? row[C + c] : 0.f;
+      m[u] = ok ? row[2 * C + c] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      S += s[u];
+      Q += q[u];
+      n += m[u];
+    }
   }
-  return m;
 }
 
 __global__ void __launch_bounds__(1024) bn_merge_conv_partials_kernel(const float* __restrict__ part, int T, int C, float* __restrict__ out) {
@@ -79,12 +93,7 @@ __global__ void __launch_bounds__(1024) bn_merge_conv_partials_kernel(const floa
   Moments acc = {0.f, 0.f, 0.f};
   if (c < C) {
     float S = 0.f, Q = 0.f, n = 0.f;
-    for (int t = tl; t < T; t += 32) {
-      const float* row = part + static_cast<size_t>(t) * 3 * C;
-      S += row[c];
-      Q += row[C + c];
-      n += row[2 * C + c];
-    }
+    accumulate_rows(part, T, C, c, tl, S, Q, n);
     if (n > 0.f) {
       acc.n = n;
       acc.mean = S / n;
@@ -118,12 +127,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float*
   Moments acc = {0.f, 0.f, 0.f};
   if (c < C) {
     float S = 0.f, Q = 0.f, n = 0.f;
-    for (int t = tl; t < T; t += 32) {
-      const float* row = part + static_cast<size_t>(t) * 3 * C;
-      S += row[c];
-      Q += row[C + c];
-      n += row[2 * C + c];
-    }
+    accumulate_rows(part, T, C, c, tl, S, Q, n);
     if (n > 0.f) {
       acc.n = n;
       acc.mean = S / n;
@@ -453,7 +457,17 @@ __global__ void __launch_bounds__(1024) bn_bwd_reduce_final_kernel(const float* 
   float acc = 0.f;
   if (idx < 2 * C) {
     const int which = idx / C, c = idx - which * C;
-    for (int t = tl; t < chunks; t += 32) acc += part[(static_cast<size_t>(t) * 2 + which) * C + c];
+    constexpr int U = 8;
+    for (int t0 = tl; t0 < chunks; t0 += 32 * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + 32 * u;
+        v[u] = t < chunks ? part[(static_cast<size_t>(t) * 2 + which) * C + c] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc += v[u];
+    }
   }
   sm[tl][cl] = acc;
   __syncthreads();
@@ -659,12 +673,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_p2p_kernel(const float* __re
   Moments acc = {0.f, 0.f, 0.f};
   if (c < C) {
     float S = 0.f, Q = 0.f, n = 0.f;
-    for (int t = tl; t < T; t += 32) {
-      const float* row = part + static_cast<size_t>(t) * 3 * C;
-      S += row[c];
-      Q += row[C + c];
-      n += row[2 * C + c];
-    }
+    accumulate_rows(part, T, C, c, tl, S, Q, n);
     if (n > 0.f) {
       acc.n = n;
       acc.mean = S / n;
@@ -720,7 +729,17 @@ __global__ void __launch_bounds__(1024) bn_bwd_reduce_final_p2p_kernel(const flo
   float acc = 0.f;
   if (idx < 2 * C) {
     const int which = idx / C, c = idx - which * C;
-    for (int t = tl; t < chunks; t += 32) acc += part[(static_cast<size_t>(t) * 2 + which) * C + c];
+    constexpr int U = 8;
+    for (int t0 = tl; t0 < chunks; t0 += 32 * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + 32 * u;
+        v[u] = t < chunks ? part[(static_cast<size_t>(t) * 2 + which) * C + c] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc += v[u];
+    }
   }
   sm[tl][cl] = acc;
   __syncthreads();

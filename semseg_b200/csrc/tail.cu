@@ -11,9 +11,8 @@
 // fp32 values ATen computes. Interpolation order follows ATen's upsample_bilinear2d:
 //   v = l0h*(l0w*v00 + l1w*v01) + l1h*(l0w*v10 + l1w*v11).
 //
-// Backward is a deterministic gather: a CTA *owns* 3x7 low-res nodes, recomputes the softmax of every output
-// pixel in their support (32 x 64 pixels), reduces along x with warp shuffles inside the 8-pixel interval groups,
-// then along y in a fixed order. No atomics, every dlogits element is written exactly once.
+// Backward is a deterministic, separable gather (rows kernel + cols kernel, see below). No atomics, every dlogits
+// element is written exactly once.
 #include "host_common.h"
 
 namespace sb {
@@ -139,69 +138,54 @@ __global__ void upsample_ce_reduce_kernel(const float* __restrict__ partial, int
 // and one exp, no shared-memory traffic and no cross-lane reduction; lse / target of the row are staged in smem and
 // read as warp-uniform broadcasts. T is an fp32 workspace [N][Ho][w][C] (272 MB at bs16/150 classes).
 // Phase 2 (cols): one CTA per node row (n, i), threads over (j, c); fixed-order sum over the <= 15 rows in support.
-// One CTA per (n, low-res interval row i0): the two node rows i0, i0+1 of the logits are staged once in shared memory
-// and shared by the 8 output rows of the interval; the block is R row-groups of Cpad (= classes rounded to 32) threads,
-// each group walking one output row at a time.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 upsample_ce_bwd_rows_kernel(const float* __restrict__ logits, int pitch, int N, int h, int w, int C,
                             const long long* __restrict__ target, int Ho, int Wo, int ignore_index,
-                            const float* __restrict__ lse, float* __restrict__ T, int Cpad, int R) {
+                            const float* __restrict__ lse, float* __restrict__ T) {
   extern __shared__ float sm[];
-  float* L0 = sm;                   // [w][C] node row i0
-  float* L1 = L0 + w * C;           // [w][C] node row i1
-  float* rowbuf = L1 + w * C;       // [R][2*Wo]: lse then target (as int) of the row a group is working on
-  const int i0 = blockIdx.x, n = blockIdx.y;
-  const int i1 = min(i0 + 1, h - 1);
-  const int rg = threadIdx.x / Cpad;          // row group
-  const int c = threadIdx.x - rg * Cpad;      // class
-  {
-    const float* g0 = logits + (static_cast<size_t>(n) * h + i0) * w * pitch;
-    const float* g1 = logits + (static_cast<size_t>(n) * h + i1) * w * pitch;
-    for (int idx = threadIdx.x; idx < w * C; idx += blockDim.x) {
-      const int j = idx / C, cc = idx - j * C;
-      L0[idx] = g0[static_cast<size_t>(j) * pitch + cc];
-      L1[idx] = g1[static_cast<size_t>(j) * pitch + cc];
-    }
+  float* s_lse = sm;                                   // [Wo]
+  int* s_t = reinterpret_cast<int*>(sm + Wo);          // [Wo], -1 = ignored
+  const int y = blockIdx.x, n = blockIdx.y;
+  const size_t rowbase = (static_cast<size_t>(n) * Ho + y) * Wo;
+  for (int x = threadIdx.x; x < Wo; x += blockDim.x) {
+    const long long t = target[rowbase + x];
+    s_t[x] = (t == ignore_index || t < 0 || t >= C) ? -1 : static_cast<int>(t);
+    s_lse[x] = lse[rowbase + x];
   }
   __syncthreads();
-  float* s_lse = rowbuf + rg * 2 * Wo;
-  int* s_t = reinterpret_cast<int*>(s_lse + Wo);
-  const int y_end = min(8 * i0 + 8, Ho);
-  for (int y = 8 * i0 + rg; y < y_end; y += R) {   // (for the last node row only y = Ho-1 exists)
-    const size_t rowbase = (static_cast<size_t>(n) * Ho + y) * Wo;
-    asm volatile("bar.sync %0, %1;" ::"r"(rg + 1), "r"(Cpad) : "memory");   // previous row's readers are done
-    for (int x = c; x < Wo; x += Cpad) {
-      const long long t = target[rowbase + x];
-      s_t[x] = (t == ignore_index || t < 0 || t >= C) ? -1 : static_cast<int>(t);
-      s_lse[x] = lse[rowbase + x];
-    }
-    asm volatile("bar.sync %0, %1;" ::"r"(rg + 1), "r"(Cpad) : "memory");
-    if (c >= C) continue;   // (group barriers above are reached by all Cpad threads; this row needs no more of them)
-    const float l1h = static_cast<float>(y & 7) * 0.125f, l0h = 1.f - l1h;
-    float* Trow = T + ((static_cast<size_t>(n) * Ho + y) * w) * C + c;
-    float a = L0[c], cc0 = L1[c];
-    float carry = 0.f;
-    for (int j0 = 0; j0 < w; ++j0) {
-      const int j1 = min(j0 + 1, w - 1);
-      const float b = L0[j1 * C + c], d = L1[j1 * C + c];
-      float accL = 0.f, accR = 0.f;
-      const int xb = j0 * 8;
-      const int xe = min(xb + 8, Wo);
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const int i0 = y >> 3;
+  const int i1 = min(i0 + 1, h - 1);
+  const float l1h = static_cast<float>(y & 7) * 0.125f, l0h = 1.f - l1h;
+  const float* L0 = logits + (static_cast<size_t>(n) * h + i0) * w * pitch + c;
+  const float* L1 = logits + (static_cast<size_t>(n) * h + i1) * w * pitch + c;
+  float* Trow = T + ((static_cast<size_t>(n) * Ho + y) * w) * C + c;
+  float a = L0[0], cc = L1[0];      // left node column of the current interval (rows i0 / i1)
+  float nb = L0[static_cast<size_t>(min(1, w - 1)) * pitch], nd = L1[static_cast<size_t>(min(1, w - 1)) * pitch];
+  float carry = 0.f;                // right-node contribution of the previous interval
+  for (int j0 = 0; j0 < w; ++j0) {
+    const float b = nb, d = nd;     // right node column (j1 = min(j0+1, w-1))
+    const int jn = min(j0 + 2, w - 1);
+    nb = L0[static_cast<size_t>(jn) * pitch];          // prefetch the next interval's right column
+    nd = L1[static_cast<size_t>(jn) * pitch];
+    float accL = 0.f, accR = 0.f;
+    const int xb = j0 * 8;
+    const int xe = min(xb + 8, Wo);
 #pragma unroll 8
-      for (int x = xb; x < xe; ++x) {
-        const int t = s_t[x];
-        if (t < 0) continue;  // warp-uniform
-        const float l1w = static_cast<float>(x & 7) * 0.125f, l0w = 1.f - l1w;
-        const float v = l0h * (l0w * a + l1w * b) + l1h * (l0w * cc0 + l1w * d);
-        const float g = __expf(v - s_lse[x]) - (c == t ? 1.f : 0.f);
-        accL = fmaf(l0w, g, accL);
-        accR = fmaf(l1w, g, accR);
-      }
-      Trow[static_cast<size_t>(j0) * C] = carry + accL;
-      carry = accR;
-      a = b;
-      cc0 = d;
+    for (int x = xb; x < xe; ++x) {
+      const int t = s_t[x];
+      if (t < 0) continue;  // warp-uniform
+      const float l1w = static_cast<float>(x & 7) * 0.125f, l0w = 1.f - l1w;
+      const float v = l0h * (l0w * a + l1w * b) + l1h * (l0w * cc + l1w * d);
+      const float g = __expf(v - s_lse[x]) - (c == t ? 1.f : 0.f);
+      accL = fmaf(l0w, g, accL);
+      accR = fmaf(l1w, g, accR);
     }
+    Trow[static_cast<size_t>(j0) * C] = carry + accL;
+    carry = accR;
+    a = b;
+    cc = d;
   }
 }
 
@@ -277,20 +261,10 @@ extern "C" int semseg_upsample_ce_bwd(const float* logits, int pitch, int N, int
   int r = check_tail(logits, pitch, N, h, w, C, target, Ho, Wo);
   if (r) return r;
   SB_CHECK_ARG(lse && loss_info && grad_out && dlogits && workspace, "upsample_ce_bwd: null pointer");
-  const int Cpad = (C + 31) / 32 * 32;
-  int R = 1024 / Cpad;
-  if (R > 4) R = 4;   // 8 output rows per interval: 4 groups x 2 rows keeps the groups balanced
-  if (R < 1) R = 1;
-  const size_t smem = (static_cast<size_t>(2) * w * C + static_cast<size_t>(R) * 2 * Wo) * sizeof(float);
-  SB_CHECK_ARG(smem <= 227 * 1024, "upsample_ce_bwd: %d classes x %d columns do not fit shared memory", C, w);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    SB_CUDA(cudaFuncSetAttribute(upsample_ce_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
-  upsample_ce_bwd_rows_kernel<<<dim3(h, N), Cpad * R, smem, stream>>>(
-      logits, pitch, N, h, w, C, reinterpret_cast<const long long*>(target), Ho, Wo, ignore_index, lse, workspace,
-      Cpad, R);
+  const int threads = (C + 31) / 32 * 32;
+  const size_t smem = static_cast<size_t>(Wo) * 8;
+  upsample_ce_bwd_rows_kernel<<<dim3(Ho, N), threads, smem, stream>>>(
+      logits, pitch, N, h, w, C, reinterpret_cast<const long long*>(target), Ho, Wo, ignore_index, lse, workspace);
   SB_LAUNCHED();
   upsample_ce_bwd_cols_kernel<<<dim3(h, N), 256, 0, stream>>>(workspace, N, h, w, C, Ho, loss_info, grad_out, dlogits);
   SB_LAUNCHED();

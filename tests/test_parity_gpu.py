@@ -218,7 +218,7 @@ def test_peer_exchange_kernels_world_of_one():
 
     px = LocalExchange()
     g = torch.Generator(device="cuda").manual_seed(5)
-    for it, c in enumerate([64, 256, 2048, 96] * 3):
+    for it, c in enumerate([64, 256, 2048, 128] * 3):
         n, h, w = 2, 12, 11
         x = (torch.randn((n, h, w, c), device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
         gamma = torch.rand((c,), device="cuda", generator=g) + 0.5

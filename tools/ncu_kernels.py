@@ -36,6 +36,15 @@ def main():
     w1 = torch.randn((2048, 512, 1, 1), device="cuda", generator=g) * 0.05
     pw1 = ops.pack_weights(w1)
     raw, sp = ops.conv_fprop(x512, pw1.wf, 2048, ops.conv_taps(1, 1), stats=True)
+    # 1x1 2048->512 (K = 2048) and the layer1 3x3 64->64 at 119x119 (multi-tap wgrad units)
+    x2048 = act(2048)
+    w2 = torch.randn((512, 2048, 1, 1), device="cuda", generator=g) * 0.02
+    ops.conv_fprop(x2048, ops.pack_weights(w2).wf, 512, ops.conv_taps(1, 1), stats=True)
+    x64, dy64 = act(64, 119), act(64, 119)
+    w64 = torch.randn((64, 64, 3, 3), device="cuda", generator=g) * 0.05
+    pw64 = ops.pack_weights(w64)
+    ops.conv_fprop(x64, pw64.wf, 64, ops.conv_taps(3, 1), stats=True)
+    ops.conv_wgrad(x64, dy64, 64, 64, ops.conv_taps(3, 1))
     # BN kernels on [16,60,60,2048]
     gamma = torch.ones(2048, device="cuda")
     beta = torch.zeros(2048, device="cuda")
@@ -45,6 +54,9 @@ def main():
     dy = act(2048)
     sums = ops.bn_bwd_reduce(dy, y, raw, mi, True)
     ops.bn_bwd_apply(dy, y, raw, mi, gamma, sums, float(n * hw * hw), True, want_dres=True)
+    # no-residual form: ReLU mask recomputed from the raw conv output, y is never read
+    sums2 = ops.bn_bwd_reduce(dy, None, raw, mi, True, scale_shift=ss)
+    ops.bn_bwd_apply(dy, None, raw, mi, gamma, sums2, float(n * hw * hw), True, scale_shift=ss)
     # fused tail
     logits = torch.randn((n, hw, hw, 150), device="cuda", generator=g)
     target = torch.randint(0, 150, (n, 473, 473), device="cuda", generator=g)
