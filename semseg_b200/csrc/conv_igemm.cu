@@ -13,8 +13,11 @@
 //   warp 1   : MMA issuer     — one elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16),
 //                               accumulators live in TMEM (2 stages so the epilogue overlaps the next tile).
 //   warps 2-5: epilogue       — tcgen05.ld -> registers -> (affine / ReLU / residual) -> bf16 ->
-//                               swizzled smem -> TMA store; per-tile BatchNorm partial statistics
-//                               (sum, M2 about the tile mean) of the stored bf16 values.
+//   (+ 6-9)                     swizzled smem -> TMA store; running BatchNorm statistics (sum, sum of squares,
+//                               count per channel) of the stored bf16 values, one row per TMEM lane quarter.
+//                               With kEpiGroups = 2 a second warpgroup takes every other 64-column chunk of the
+//                               tile (own staging buffer, own named barrier): the 1x1 convs with wide outputs are
+//                               epilogue-bound and a single warp per scheduler cannot hide its own latencies.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -22,8 +25,8 @@ namespace sb {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle span
-constexpr int kNumThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiGroupThreads = 128;  // one epilogue warpgroup = 4 warps = the 4 TMEM lane quarters
+constexpr int conv_threads(int epi_groups) { return 64 + epi_groups * kEpiGroupThreads; }
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kStageOutBytes = kBlockM * 64 * 2;    // 16 KB epilogue staging chunk (64 columns)
 constexpr int kMiscBytes = 2048;
@@ -66,11 +69,14 @@ struct ConvKParams {
 // BLOCK_N=256) and the freed smem buys more pipeline stages. TMA completions of both CTAs are credited to the leader's
 // full barrier; the leader's tcgen05.commit is multicast to both CTAs' empty / tmem_full barriers; the peer's epilogue
 // hands its accumulator stage back by arriving on the leader's tmem_empty barrier.
-template <int BLOCK_N, bool kCluster>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int BLOCK_N, bool kCluster, int kEpiGroups>
+__global__ void __launch_bounds__(conv_threads(kEpiGroups), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const ConvKParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
+  constexpr int kNumThreads = conv_threads(kEpiGroups);
+  constexpr int kEpiThreads = kEpiGroups * kEpiGroupThreads;
+  static_assert(kEpiGroups == 1 || kEpiGroups == 2, "one or two epilogue warpgroups");
   constexpr int kStages = kCluster ? Cfg::kPairStages : Cfg::kStages;
   constexpr int kStageBytes = kCluster ? Cfg::kPairStageBytes : Cfg::kStageBytes;
   const uint32_t cta_rank = kCluster ? cluster_ctarank() : 0u;
@@ -219,10 +225,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
-    const int g = warp & 3;             // TMEM lane group this warp may access
+    // ===================================================================== epilogue (warps 2..5 and, two groups, 6..9)
+    const int g = warp & 3;             // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
     const int row = g * 32 + lane;      // accumulator row == pixel within the tile
-    const int et = (warp - 2) * 32 + lane;  // 0..127
+    const int grp = (warp - 2) >> 2;    // epilogue warpgroup: chunks grp, grp + kEpiGroups, ... of every tile
+    const int et = ((warp - 2) & 3) * 32 + lane;  // 0..127 inside the group
+    const uint32_t bar_id = 1u + static_cast<uint32_t>(grp);
     int tile_iter = 0;
     int store_buf = 0;
     for (int item = item_first; item < num_items; item += item_step, ++tile_iter) {
@@ -255,7 +263,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       constexpr int kChunks = BLOCK_N / 64;
 #pragma unroll 1
-      for (int ch = 0; ch < kChunks; ++ch) {
+      for (int ch = grp; ch < kChunks; ch += kEpiGroups) {
         const int c0 = n0 + ch * 64;  // first output channel of this chunk
         if (c0 >= p.Cout) break;      // (uniform) nothing to write for padded columns
         // Prefetch this CTA's running statistics for the chunk's columns now; the read-modify-write below then
@@ -333,9 +341,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
 
         // registers -> bf16 -> 128B-swizzled staging tile (row = pixel, 64 channels = 128 bytes)
-        uint8_t* obuf = out_stage + store_buf * kStageOutBytes;
-        if (et == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained
-        named_bar_sync(1, kEpiThreads);
+        // one group: two staging buffers used alternately; two groups: one buffer each
+        uint8_t* obuf = out_stage + (kEpiGroups == 1 ? store_buf : grp) * kStageOutBytes;
+        if (et == 0) tma_store_wait_read<(kEpiGroups == 1 ? 1 : 0)>();  // the store that last read this buffer has drained
+        named_bar_sync(bar_id, kEpiGroupThreads);
 #pragma unroll
         for (int j8 = 0; j8 < 8; ++j8) {
           uint4 o;
@@ -356,18 +365,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
           const uint8_t* base = obuf + (lane & 3) * 4;
           const int chunk16 = lane >> 2;
+          auto add_row = [&](int rr, int sw) {  // sw = rr & 7 (the row's swizzle phase)
+            const __nv_bfloat162 bv =
+                *reinterpret_cast<const __nv_bfloat162*>(base + rr * 128 + ((chunk16 ^ sw) << 4));
+            const float2 f = __bfloat1622float2(bv);
+            s0 += f.x;
+            s1 += f.y;
+            q0 = fmaf(f.x, f.x, q0);
+            q1 = fmaf(f.y, f.y, q1);
+          };
+          if ((row_msk & (row_msk + 1u)) == 0u) {
+            // valid rows are a prefix of the warp's 32 (always, unless the box is clipped by the right image edge):
+            // whole groups of 8 rows run without per-row predicates, the swizzle phase is a compile-time constant
+            const int nr = __popc(row_msk);
+            const int nfull = nr >> 3;
+            for (int b8 = 0; b8 < nfull; ++b8) {
+              const int rr0 = g * 32 + b8 * 8;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const int rr = g * 32 + r;
-            if ((row_msk >> r) & 1u) {
-              const __nv_bfloat162 bv =
-                  *reinterpret_cast<const __nv_bfloat162*>(base + rr * 128 + ((chunk16 ^ (rr & 7)) << 4));
-              const float2 f = __bfloat1622float2(bv);
-              s0 += f.x;
-              s1 += f.y;
-              q0 = fmaf(f.x, f.x, q0);
-              q1 = fmaf(f.y, f.y, q1);
+              for (int k = 0; k < 8; ++k) add_row(rr0 + k, k);
             }
+            for (int r = nfull * 8; r < nr; ++r) add_row(g * 32 + r, r & 7);
+          } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if ((row_msk >> r) & 1u) add_row(g * 32 + r, r & 7);
           }
           const float nt = static_cast<float>(__popc(row_msk));
           st_dst[0] = st_old[0] + s0;
@@ -377,7 +398,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           st_dst[2 * p.Cout] = st_old[4] + nt;
           st_dst[2 * p.Cout + 1] = st_old[5] + nt;
         }
-        named_bar_sync(1, kEpiThreads);
+        named_bar_sync(bar_id, kEpiGroupThreads);
         if (et == 0) {
           tma_store_4d(&tmC, obuf, c0, w0, h0, img);
           tma_store_commit();
@@ -425,24 +446,35 @@ static int conv_grid(int num_m_tiles, int n_tiles, bool* clustered) {
   return static_cast<int>(2 * (items < max_clusters ? items : max_clusters));
 }
 
-template <int BLOCK_N>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvKParams& kp,
-                       bool clustered, int grid, cudaStream_t stream) {
+// Two epilogue warpgroups by default for tiles with >= 2 column chunks (SEMSEG_B200_EPI_GROUPS=1 keeps one).
+static int epi_groups_wanted() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEMSEG_B200_EPI_GROUPS");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
+template <int BLOCK_N, int kEpiGroups>
+static int launch_conv_g(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvKParams& kp,
+                         bool clustered, int grid, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::kSmemBytes));
-    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::kSmemBytes));
+    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, false, kEpiGroups>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, true, kEpiGroups>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
+  constexpr int kThreads = conv_threads(kEpiGroups);
   if (!clustered) {
-    conv_igemm_kernel<BLOCK_N, false><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, kp);
+    conv_igemm_kernel<BLOCK_N, false, kEpiGroups><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, kp);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kNumThreads);
+    cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -452,10 +484,19 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, true>, tmA, tmB, tmC, kp));
+    SB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, true, kEpiGroups>, tmA, tmB, tmC, kp));
   }
   SB_LAUNCHED();
   return SEMSEG_OK;
+}
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvKParams& kp,
+                       bool clustered, int grid, cudaStream_t stream) {
+  if constexpr (BLOCK_N >= 128) {
+    if (epi_groups_wanted() == 2) return launch_conv_g<BLOCK_N, 2>(tmA, tmB, tmC, kp, clustered, grid, stream);
+  }
+  return launch_conv_g<BLOCK_N, 1>(tmA, tmB, tmC, kp, clustered, grid, stream);
 }
 
 }  // namespace sb

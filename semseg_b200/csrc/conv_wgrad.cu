@@ -283,17 +283,43 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int n_splits, int taps, int Cout, int Cin,
+// part[s][t][co][ci] -> dw[co][ci][t], splits added in order s = 0, 1, ... (fixed order => deterministic).
+// block = (32 plane lanes, taps, G groups): reads are 128-byte rows of one (split, tap) plane, four splits in flight;
+// the [tap][lane] tile is turned through shared memory so the OIHW writes are contiguous too.
+constexpr int kRedMaxTaps = 9;
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int n_splits, int taps, size_t plane,
                                     float* __restrict__ dw, int accumulate) {
-  // one thread per (co, ci); loops taps. part[s][t][co][ci] -> dw[co][ci][t]
-  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t plane = static_cast<size_t>(Cout) * Cin;
-  if (idx >= plane) return;
-  for (int t = 0; t < taps; ++t) {
-    float s = 0.f;
-    for (int sp = 0; sp < n_splits; ++sp) s += part[(static_cast<size_t>(sp) * taps + t) * plane + idx];
-    float* d = dw + idx * taps + t;
-    *d = accumulate ? (*d + s) : s;
+  extern __shared__ float red_tile[];  // [G][taps][33]
+  const int lane = threadIdx.x, t = threadIdx.y, grp = threadIdx.z;
+  float* tile = red_tile + grp * taps * 33;
+  const size_t idx0 = (static_cast<size_t>(blockIdx.x) * blockDim.z + grp) * 32;
+  const size_t idx = idx0 + lane;
+  float s = 0.f;
+  if (idx < plane) {
+    const size_t stride = static_cast<size_t>(taps) * plane;
+    const float* p = part + static_cast<size_t>(t) * plane + idx;
+    int sp = 0;
+    for (; sp + 4 <= n_splits; sp += 4) {
+      const float a = p[0], b = p[stride], c = p[2 * stride], d = p[3 * stride];
+      s += a;
+      s += b;
+      s += c;
+      s += d;
+      p += 4 * stride;
+    }
+    for (; sp < n_splits; ++sp) {
+      s += *p;
+      p += stride;
+    }
+  }
+  tile[t * 33 + lane] = s;
+  __syncthreads();
+  const int j = t * 32 + lane;  // position inside this group's 32*taps contiguous outputs
+  const int l = j / taps, tt = j - l * taps;
+  if (idx0 + l < plane) {
+    float* d = dw + idx0 * taps + j;
+    const float v = tile[tt * 33 + l];
+    *d = accumulate ? (*d + v) : v;
   }
 }
 
@@ -443,10 +469,14 @@ extern "C" int semseg_wgrad_reduce(const float* dw_partial, int n_splits, int ta
   using namespace sb;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(dw_partial && dw_oihw && n_splits > 0 && taps > 0 && Cout > 0 && Cin > 0, "wgrad_reduce: bad args");
+  SB_CHECK_ARG(taps <= kRedMaxTaps, "wgrad_reduce: at most 9 taps");
   const size_t plane = static_cast<size_t>(Cout) * Cin;
-  const int threads = 256;
-  const unsigned blocks = static_cast<unsigned>((plane + threads - 1) / threads);
-  wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(dw_partial, n_splits, taps, Cout, Cin, dw_oihw, accumulate);
+  const int groups = taps >= 8 ? 1 : 8 / taps;
+  const dim3 block(32, taps, groups);
+  const size_t per_block = static_cast<size_t>(32) * groups;
+  const unsigned blocks = static_cast<unsigned>((plane + per_block - 1) / per_block);
+  const size_t smem = static_cast<size_t>(groups) * taps * 33 * sizeof(float);
+  wgrad_reduce_kernel<<<blocks, block, smem, stream>>>(dw_partial, n_splits, taps, plane, dw_oihw, accumulate);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }

@@ -148,7 +148,10 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m,
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  // default semantics (release at CTA scope): the consumer only needs the arrival itself — the TMEM reads it guards are
+  // complete (tcgen05.wait::ld + tcgen05.fence::before_thread_sync) — and a cluster-scope release would make every
+  // epilogue warp wait for all of its earlier global stores (MEMBAR.ALL.GPU) once per tile.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
