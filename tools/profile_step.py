@@ -78,6 +78,15 @@ def main():
     lines.append("total kernel time %.2f ms over %d launches" % (tot / 1e3, sum(v[1] for v in agg.values())))
     for name, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
         lines.append("%8.3f ms %5.1f%% x%-4d %s" % (t / 1e3, 100 * t / tot, c, name[:110]))
+    # per-launch spread of the short, many-launch kernels (latency-bound candidates)
+    per = {}
+    for e in ev:
+        per.setdefault(e.name, []).append(e.device_time)
+    for name, ts in per.items():
+        if len(ts) >= 16 and any(k in name for k in ("wgrad_reduce", "bn_finalize", "bn_bwd_reduce_final", "pack_w")):
+            ts = sorted(ts)
+            lines.append("  spread %-40s min %.1f  median %.1f  p90 %.1f  max %.1f us" %
+                         (name.split("(")[0][-40:], ts[0], ts[len(ts) // 2], ts[int(len(ts) * 0.9)], ts[-1]))
     txt = "\n".join(lines)
     print(txt)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
