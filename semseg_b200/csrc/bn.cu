@@ -57,54 +57,74 @@ __global__ void __launch_bounds__(1024) bn_merge_partials_kernel(const float* __
 
 // The conv epilogue's statistics buffer is [rows][3][C] = (sum, sum of squares, count) per epilogue warp.
 
-// Adds the raw (sum, sum of squares, count) of rows tl, tl+32, ... for channel c. The rows are independent loads, so
-// eight rows (24 loads) are issued before the first add: the kernel is a chain of ~T/256 memory round trips instead
-// of T/32.
-__device__ __forceinline__ void accumulate_rows(const float* __restrict__ part, int T, int C, int c, int tl, float& S,
-                                                float& Q, float& n) {
+// Block-wide merge of the conv statistics rows for CH channels starting at c0. A block is 1024 threads = CH channels x
+// (1024 / CH) row lanes; narrow channel groups (CH = 8) spread a layer over more blocks / SMs, which is what bounds this
+// kernel (each block pulls rows * 3 * CH floats out of L2). Every thread issues all of its row loads (up to 8 rows = 24
+// loads) before the first add; raw (sum, sum of squares, count) are added over a thread's rows and over the row lanes of
+// its warp (butterfly), converted once to (mean, M2, n) and the 32 warps are merged with Chan's formula in fixed order.
+// Result: valid in threads threadIdx.x < CH for channel c0 + threadIdx.x.
+template <int CH>
+__device__ __forceinline__ Moments block_conv_moments(const float* __restrict__ part, int T, int C, int c0,
+                                                      Moments (*sm)[CH + 1]) {
+  constexpr int RL = 1024 / CH;  // row lanes per block
   constexpr int U = 8;
-  for (int t0 = tl; t0 < T; t0 += 32 * U) {
-    float s[U], q[U], m[U];
+  const int cl = threadIdx.x % CH;
+  const int rl = threadIdx.x / CH;
+  const int c = c0 + cl;
+  float S = 0.f, Q = 0.f, n = 0.f;
+  if (c < C) {
+    for (int t0 = rl; t0 < T; t0 += RL * U) {
+      float s[U], q[U], m[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int t = t0 + 32 * u;
-      const bool ok = t < T;
-      const float* row = part + static_cast<size_t>(ok ? t : 0) * 3 * C;
-      s[u] = ok ? row[c] : 0.f;
-      q[u] = ok ? row[C + c] : 0.f;
-      m[u] = ok ? row[2 * C + c] : 0.f;
-    }
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + RL * u;
+        const bool ok = t < T;
+        const float* row = part + static_cast<size_t>(ok ? t : 0) * 3 * C;
+        s[u] = ok ? row[c] : 0.f;
+        q[u] = ok ? row[C + c] : 0.f;
+        m[u] = ok ? row[2 * C + c] : 0.f;
+      }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      S += s[u];
-      Q += q[u];
-      n += m[u];
+      for (int u = 0; u < U; ++u) {
+        S += s[u];
+        Q += q[u];
+        n += m[u];
+      }
     }
   }
+#pragma unroll
+  for (int o = CH; o < 32; o <<= 1) {  // lanes cl, cl + CH, ... of a warp hold the same channel
+    S += __shfl_xor_sync(0xffffffffu, S, o);
+    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+  }
+  Moments acc = {0.f, 0.f, 0.f};
+  if (n > 0.f) {
+    acc.n = n;
+    acc.mean = S / n;
+    acc.m2 = fmaxf(Q - S * acc.mean, 0.f);
+  }
+  if ((threadIdx.x & 31) < CH) sm[threadIdx.x >> 5][cl] = acc;
+  __syncthreads();
+  Moments r = {0.f, 0.f, 0.f};
+  if (threadIdx.x < CH) {
+    r = sm[0][threadIdx.x];
+    for (int i = 1; i < 32; ++i) r = merge(r, sm[i][threadIdx.x]);
+  }
+  return r;
 }
 
-__global__ void __launch_bounds__(1024) bn_merge_conv_partials_kernel(const float* __restrict__ part, int T, int C, float* __restrict__ out) {
-  __shared__ Moments sm[32][33];
-  const int cl = threadIdx.x & 31;
-  const int tl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  // each lane adds the raw (sum, sum of squares, count) of its rows (no divisions), converts once to moments;
-  // the 32 lanes are then merged with Chan's formula in a fixed order
-  Moments acc = {0.f, 0.f, 0.f};
-  if (c < C) {
-    float S = 0.f, Q = 0.f, n = 0.f;
-    accumulate_rows(part, T, C, c, tl, S, Q, n);
-    if (n > 0.f) {
-      acc.n = n;
-      acc.mean = S / n;
-      acc.m2 = fmaxf(Q - S * acc.mean, 0.f);
-    }
-  }
-  sm[tl][cl] = acc;
-  __syncthreads();
-  if (tl == 0 && c < C) {
-    Moments r = sm[0][cl];
-    for (int i = 1; i < 32; ++i) r = merge(r, sm[i][cl]);
+// Channels per block such that a layer needs at most 128 blocks (one wave; the peer-exchange kernels additionally
+// need all of their blocks co-resident because they spin on the peers' flags).
+static int stats_group_channels(int C) { return C <= 1024 ? 8 : (C <= 2048 ? 16 : 32); }
+
+template <int CH>
+__global__ void __launch_bounds__(1024) bn_merge_conv_partials_kernel(const float* __restrict__ part, int T, int C,
+                                                                      float* __restrict__ out) {
+  __shared__ Moments sm[32][CH + 1];
+  const Moments r = block_conv_moments<CH>(part, T, C, blockIdx.x * CH, sm);
+  const int c = blockIdx.x * CH + threadIdx.x;
+  if (threadIdx.x < CH && c < C) {
     out[c] = r.mean;
     out[C + c] = r.m2;
     out[2 * C + c] = r.n;
@@ -113,32 +133,16 @@ __global__ void __launch_bounds__(1024) bn_merge_conv_partials_kernel(const floa
 
 // ------------------------------------------------------------------------------------------------
 // Single-rank fast path: merge the per-tile partials AND finalise in one launch (no SyncBN exchange needed).
+template <int CH>
 __global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float* __restrict__ part, int T, int C,
                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                             float eps, float momentum, float* __restrict__ running_mean,
                                             float* __restrict__ running_var, float* __restrict__ mean_invstd,
                                             float* __restrict__ scale_shift) {
-  __shared__ Moments sm[32][33];
-  const int cl = threadIdx.x & 31;
-  const int tl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  // each lane adds the raw (sum, sum of squares, count) of its rows (no divisions), converts once to moments;
-  // the 32 lanes are then merged with Chan's formula in a fixed order
-  Moments acc = {0.f, 0.f, 0.f};
-  if (c < C) {
-    float S = 0.f, Q = 0.f, n = 0.f;
-    accumulate_rows(part, T, C, c, tl, S, Q, n);
-    if (n > 0.f) {
-      acc.n = n;
-      acc.mean = S / n;
-      acc.m2 = fmaxf(Q - S * acc.mean, 0.f);
-    }
-  }
-  sm[tl][cl] = acc;
-  __syncthreads();
-  if (tl == 0 && c < C) {
-    Moments r = sm[0][cl];
-    for (int i = 1; i < 32; ++i) r = merge(r, sm[i][cl]);
+  __shared__ Moments sm[32][CH + 1];
+  const Moments r = block_conv_moments<CH>(part, T, C, blockIdx.x * CH, sm);
+  const int c = blockIdx.x * CH + threadIdx.x;
+  if (threadIdx.x < CH && c < C) {
     const float var = r.n > 0.f ? r.m2 / r.n : 0.f;
     const float invstd = rsqrtf(var + eps);
     mean_invstd[c] = r.mean;
@@ -660,39 +664,24 @@ __device__ __forceinline__ void peer_publish_and_wait(const PeerArgs& pa) {
 }
 
 // Forward: merge this rank's conv partials, exchange (mean, M2, n), merge over ranks, finalise.
+template <int CH>
 __global__ void __launch_bounds__(1024) bn_finalize_p2p_kernel(const float* __restrict__ part, int T, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, float momentum,
                                        float* __restrict__ running_mean, float* __restrict__ running_var,
                                        float* __restrict__ mean_invstd, float* __restrict__ scale_shift, PeerArgs pa) {
-  __shared__ Moments sm[32][33];
-  const int cl = threadIdx.x & 31;
-  const int tl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  // each lane adds the raw (sum, sum of squares, count) of its rows (no divisions), converts once to moments;
-  // the 32 lanes are then merged with Chan's formula in a fixed order
-  Moments acc = {0.f, 0.f, 0.f};
-  if (c < C) {
-    float S = 0.f, Q = 0.f, n = 0.f;
-    accumulate_rows(part, T, C, c, tl, S, Q, n);
-    if (n > 0.f) {
-      acc.n = n;
-      acc.mean = S / n;
-      acc.m2 = fmaxf(Q - S * acc.mean, 0.f);
-    }
-  }
-  sm[tl][cl] = acc;
-  __syncthreads();
+  __shared__ Moments sm[32][CH + 1];
+  const Moments own_m = block_conv_moments<CH>(part, T, C, blockIdx.x * CH, sm);
+  const int c = blockIdx.x * CH + threadIdx.x;
+  const bool fin = threadIdx.x < CH && c < C;  // this thread finishes channel c
   const size_t off = static_cast<size_t>(pa.slot) * pa.slot_floats;
-  if (tl == 0 && c < C) {
-    Moments r = sm[0][cl];
-    for (int i = 1; i < 32; ++i) r = merge(r, sm[i][cl]);
+  if (fin) {
     float* own = pa.buf[pa.rank] + off;
-    own[c] = r.mean;
-    own[C + c] = r.m2;
-    own[2 * C + c] = r.n;
+    own[c] = own_m.mean;
+    own[C + c] = own_m.m2;
+    own[2 * C + c] = own_m.n;
   }
   peer_publish_and_wait(pa);
-  if (tl == 0 && c < C) {
+  if (fin) {
     Moments r = {0.f, 0.f, 0.f};
     for (int p = 0; p < pa.world; ++p) {
       const float* b = pa.buf[p] + off;
@@ -797,7 +786,11 @@ extern "C" long long semseg_bn_workspace_floats(int M, int C) {
 extern "C" int semseg_bn_merge_partials(const float* stats_partial, int rows, int C, float* out_stats, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(stats_partial && out_stats && rows > 0 && C > 0, "bn_merge_partials: bad args");
-  bn_merge_conv_partials_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, rows, C, out_stats);
+  switch (stats_group_channels(C)) {
+    case 8: bn_merge_conv_partials_kernel<8><<<cdiv(C, 8), 1024, 0, stream>>>(stats_partial, rows, C, out_stats); break;
+    case 16: bn_merge_conv_partials_kernel<16><<<cdiv(C, 16), 1024, 0, stream>>>(stats_partial, rows, C, out_stats); break;
+    default: bn_merge_conv_partials_kernel<32><<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, rows, C, out_stats); break;
+  }
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
@@ -809,9 +802,11 @@ extern "C" int semseg_bn_finalize_partials(const float* stats_partial, int num_t
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(stats_partial && mean_invstd && scale_shift && num_tiles > 0 && C > 0,
                "bn_finalize_partials: bad args");
-  bn_finalize_partials_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, num_tiles, C, gamma, beta,
-                                                               eps, momentum, running_mean, running_var, mean_invstd,
-                                                               scale_shift);
+  switch (stats_group_channels(C)) {
+    case 8: bn_finalize_partials_kernel<8><<<cdiv(C, 8), 1024, 0, stream>>>(stats_partial, num_tiles, C, gamma, beta, eps, momentum, running_mean, running_var, mean_invstd, scale_shift); break;
+    case 16: bn_finalize_partials_kernel<16><<<cdiv(C, 16), 1024, 0, stream>>>(stats_partial, num_tiles, C, gamma, beta, eps, momentum, running_mean, running_var, mean_invstd, scale_shift); break;
+    default: bn_finalize_partials_kernel<32><<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, num_tiles, C, gamma, beta, eps, momentum, running_mean, running_var, mean_invstd, scale_shift); break;
+  }
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
@@ -969,8 +964,11 @@ extern "C" int semseg_bn_finalize_p2p(const float* stats_partial, int rows, int 
   sb::PeerArgs pa;
   int r = fill_peer_args(&pa, peer_bufs, peer_flags, counter, world, rank, slot, slot_floats, seq, 3 * C);
   if (r) return r;
-  bn_finalize_p2p_kernel<<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, rows, C, gamma, beta, eps, momentum,
-                                                          running_mean, running_var, mean_invstd, scale_shift, pa);
+  switch (stats_group_channels(C)) {
+    case 8: bn_finalize_p2p_kernel<8><<<cdiv(C, 8), 1024, 0, stream>>>(stats_partial, rows, C, gamma, beta, eps, momentum, running_mean, running_var, mean_invstd, scale_shift, pa); break;
+    case 16: bn_finalize_p2p_kernel<16><<<cdiv(C, 16), 1024, 0, stream>>>(stats_partial, rows, C, gamma, beta, eps, momentum, running_mean, running_var, mean_invstd, scale_shift, pa); break;
+    default: bn_finalize_p2p_kernel<32><<<cdiv(C, 32), 1024, 0, stream>>>(stats_partial, rows, C, gamma, beta, eps, momentum, running_mean, running_var, mean_invstd, scale_shift, pa); break;
+  }
   SB_LAUNCHED();
   return SEMSEG_OK;
 }

@@ -284,42 +284,71 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 }
 
 // part[s][t][co][ci] -> dw[co][ci][t], splits added in order s = 0, 1, ... (fixed order => deterministic).
-// block = (32 plane lanes, taps, G groups): reads are 128-byte rows of one (split, tap) plane, four splits in flight;
-// the [tap][lane] tile is turned through shared memory so the OIHW writes are contiguous too.
+// block = (32 plane lanes, taps, G groups): every lane owns W consecutive plane elements (W = 4: one 16-byte load per
+// split, four splits in flight), so even the single-split layers (cls head: a 75 MB transposing copy) keep enough bytes
+// in flight; the [tap][lane] tile is turned through shared memory so the OIHW writes are contiguous too.
 constexpr int kRedMaxTaps = 9;
+template <int W>
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int n_splits, int taps, size_t plane,
                                     float* __restrict__ dw, int accumulate) {
-  extern __shared__ float red_tile[];  // [G][taps][33]
+  extern __shared__ __align__(16) float red_tile[];  // [G][taps][32 * W + 4]
+  constexpr int kRow = 32 * W + 4;
   const int lane = threadIdx.x, t = threadIdx.y, grp = threadIdx.z;
-  float* tile = red_tile + grp * taps * 33;
-  const size_t idx0 = (static_cast<size_t>(blockIdx.x) * blockDim.z + grp) * 32;
-  const size_t idx = idx0 + lane;
-  float s = 0.f;
-  if (idx < plane) {
+  float* tile = red_tile + grp * taps * kRow;
+  const size_t idx0 = (static_cast<size_t>(blockIdx.x) * blockDim.z + grp) * (32 * W);
+  const size_t idx = idx0 + static_cast<size_t>(lane) * W;
+  float s[W];
+#pragma unroll
+  for (int q = 0; q < W; ++q) s[q] = 0.f;
+  if (idx < plane) {  // plane % W == 0: the whole vector is inside
     const size_t stride = static_cast<size_t>(taps) * plane;
     const float* p = part + static_cast<size_t>(t) * plane + idx;
+    auto ld = [&](const float* q, float (&v)[W]) {
+      if constexpr (W == 4) {
+        const float4 f = *reinterpret_cast<const float4*>(q);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+      } else {
+        v[0] = *q;
+      }
+    };
     int sp = 0;
     for (; sp + 4 <= n_splits; sp += 4) {
-      const float a = p[0], b = p[stride], c = p[2 * stride], d = p[3 * stride];
-      s += a;
-      s += b;
-      s += c;
-      s += d;
+      float a[W], b[W], c[W], d[W];
+      ld(p, a);
+      ld(p + stride, b);
+      ld(p + 2 * stride, c);
+      ld(p + 3 * stride, d);
+#pragma unroll
+      for (int q = 0; q < W; ++q) {
+        s[q] += a[q];
+        s[q] += b[q];
+        s[q] += c[q];
+        s[q] += d[q];
+      }
       p += 4 * stride;
     }
     for (; sp < n_splits; ++sp) {
-      s += *p;
+      float a[W];
+      ld(p, a);
+#pragma unroll
+      for (int q = 0; q < W; ++q) s[q] += a[q];
       p += stride;
     }
   }
-  tile[t * 33 + lane] = s;
+#pragma unroll
+  for (int q = 0; q < W; ++q) tile[t * kRow + lane * W + q] = s[q];
   __syncthreads();
-  const int j = t * 32 + lane;  // position inside this group's 32*taps contiguous outputs
-  const int l = j / taps, tt = j - l * taps;
-  if (idx0 + l < plane) {
-    float* d = dw + idx0 * taps + j;
-    const float v = tile[tt * 33 + l];
-    *d = accumulate ? (*d + v) : v;
+  // this group's 32*W*taps outputs are contiguous in dw; thread (t, lane) writes W of them, 32*taps apart
+  const int per = 32 * taps;
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const int j = k * per + t * 32 + lane;
+    const int l = j / taps, tt = j - l * taps;
+    if (idx0 + l < plane) {
+      float* d = dw + idx0 * taps + j;
+      const float v = tile[tt * kRow + l];
+      *d = accumulate ? (*d + v) : v;
+    }
   }
 }
 
@@ -473,10 +502,17 @@ extern "C" int semseg_wgrad_reduce(const float* dw_partial, int n_splits, int ta
   const size_t plane = static_cast<size_t>(Cout) * Cin;
   const int groups = taps >= 8 ? 1 : 8 / taps;
   const dim3 block(32, taps, groups);
-  const size_t per_block = static_cast<size_t>(32) * groups;
-  const unsigned blocks = static_cast<unsigned>((plane + per_block - 1) / per_block);
-  const size_t smem = static_cast<size_t>(groups) * taps * 33 * sizeof(float);
-  wgrad_reduce_kernel<<<blocks, block, smem, stream>>>(dw_partial, n_splits, taps, plane, dw_oihw, accumulate);
+  if (plane % 4 == 0) {
+    const size_t per_block = static_cast<size_t>(128) * groups;
+    const unsigned blocks = static_cast<unsigned>((plane + per_block - 1) / per_block);
+    const size_t smem = static_cast<size_t>(groups) * taps * (128 + 4) * sizeof(float);
+    wgrad_reduce_kernel<4><<<blocks, block, smem, stream>>>(dw_partial, n_splits, taps, plane, dw_oihw, accumulate);
+  } else {
+    const size_t per_block = static_cast<size_t>(32) * groups;
+    const unsigned blocks = static_cast<unsigned>((plane + per_block - 1) / per_block);
+    const size_t smem = static_cast<size_t>(groups) * taps * (32 + 4) * sizeof(float);
+    wgrad_reduce_kernel<1><<<blocks, block, smem, stream>>>(dw_partial, n_splits, taps, plane, dw_oihw, accumulate);
+  }
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
