@@ -226,6 +226,8 @@ int semseg_maxpool3x3s2_bwd(const void* argcode, const void* dy, void* dx, int N
  *   bins[nb] = pooled sizes (1,2,3,6); per-bin tensors are [N][b][b][channels] contiguous bf16.
  *   ppm_pool            : pooled_k = AdaptiveAvgPool2d(b_k)(x), window [floor(i*H/b), ceil((i+1)*H/b)).
  *   ppm_pool_bwd        : dx (dense, every element written) = sum_k adjoint of the pooling applied to dpooled_k.
+ *   ppm_pool_bwd        : dx = adjoint of ppm_pool (+ `add` [N,H,W,add_pitch], nullable: the identity branch of the
+ *                         concat, so the two gradients of x are summed in this kernel instead of by autograd).
  *   ppm_upsample_concat : out[..., 0:C] = x; out[..., C + k*Cr : C + (k+1)*Cr] = bilinear(align_corners=True) of
  *                         feats_k to H x W (the torch.cat of model/pspnet.py:26 written in place).
  *   ppm_upsample_bwd    : dfeats_k = adjoint of the bilinear upsample applied to dout[..., c_off + k*Cr : ...].
@@ -233,7 +235,7 @@ int semseg_maxpool3x3s2_bwd(const void* argcode, const void* dy, void* dx, int N
 int semseg_ppm_pool(const void* x, int x_pitch, int N, int H, int W, int C, const int* bins, void* const* pooled,
                     int nb, void* stream);
 int semseg_ppm_pool_bwd(void* const* dpooled, const int* bins, int nb, int N, int H, int W, int C, void* dx,
-                        int dx_pitch, void* stream);
+                        int dx_pitch, const void* add, int add_pitch, void* stream);
 int semseg_ppm_upsample_concat(const void* x, int x_pitch, void* const* feats, const int* bins, int nb, int N, int H,
                                int W, int C, int Cr, void* out, int out_pitch, void* stream);
 int semseg_ppm_upsample_bwd(const void* dout, int dout_pitch, int c_off, void* const* dfeats, const int* bins, int nb,

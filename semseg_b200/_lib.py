@@ -97,7 +97,7 @@ SIGNATURES = {
     "semseg_maxpool3x3s2_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_maxpool3x3s2_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_ppm_pool": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
-    "semseg_ppm_pool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "semseg_ppm_pool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     "semseg_ppm_upsample_concat": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                                            c_int, c_vp]),
     "semseg_ppm_upsample_bwd": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(1024) bn_merge_partials_kernel(const float* __
 // (1024 / CH) row lanes; narrow channel groups (CH = 8) spread a layer over more blocks / SMs, which is what bounds this
 // kernel (each block pulls rows * 3 * CH floats out of L2). Every thread issues all of its row loads (up to 8 rows = 24
 // loads) before the first add; raw (sum, sum of squares, count) are added over a thread's rows and over the row lanes of
-// its warp (butterfly), converted once to (mean, M2, n) and the 32 warps are merged with Chan's formula in fixed order.
-// Result: valid in threads threadIdx.x < CH for channel c0 + threadIdx.x.
+// its warp (butterfly), converted once to (mean, M2, n) and the 32 warps are merged with Chan's formula by a shuffle tree.
+// Result: valid in lane 0 of warp w < CH for channel c0 + w.
 template <int CH>
 __device__ __forceinline__ Moments block_conv_moments(const float* __restrict__ part, int T, int C, int c0,
                                                       Moments (*sm)[CH + 1]) {
@@ -106,12 +106,21 @@ __device__ __forceinline__ Moments block_conv_moments(const float* __restrict__ 
   }
   if ((threadIdx.x & 31) < CH) sm[threadIdx.x >> 5][cl] = acc;
   __syncthreads();
+  // warp w (< CH) merges channel c0 + w: lane i holds warp i's partial, 5-step shuffle tree in a fixed order
   Moments r = {0.f, 0.f, 0.f};
-  if (threadIdx.x < CH) {
-    r = sm[0][threadIdx.x];
-    for (int i = 1; i < 32; ++i) r = merge(r, sm[i][threadIdx.x]);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (w < CH) {
+    r = sm[lane][w];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Moments other;
+      other.mean = __shfl_down_sync(0xffffffffu, r.mean, o);
+      other.m2 = __shfl_down_sync(0xffffffffu, r.m2, o);
+      other.n = __shfl_down_sync(0xffffffffu, r.n, o);
+      r = merge(r, other);
+    }
   }
-  return r;
+  return r;  // valid in lane 0 of warps 0..CH-1
 }
 
 // Channels per block such that a layer needs at most 128 blocks (one wave; the peer-exchange kernels additionally
@@ -123,8 +132,8 @@ __global__ void __launch_bounds__(1024) bn_merge_conv_partials_kernel(const floa
                                                                       float* __restrict__ out) {
   __shared__ Moments sm[32][CH + 1];
   const Moments r = block_conv_moments<CH>(part, T, C, blockIdx.x * CH, sm);
-  const int c = blockIdx.x * CH + threadIdx.x;
-  if (threadIdx.x < CH && c < C) {
+  const int c = blockIdx.x * CH + (threadIdx.x >> 5);
+  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < CH && c < C) {
     out[c] = r.mean;
     out[C + c] = r.m2;
     out[2 * C + c] = r.n;
@@ -141,8 +150,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float*
                                             float* __restrict__ scale_shift) {
   __shared__ Moments sm[32][CH + 1];
   const Moments r = block_conv_moments<CH>(part, T, C, blockIdx.x * CH, sm);
-  const int c = blockIdx.x * CH + threadIdx.x;
-  if (threadIdx.x < CH && c < C) {
+  const int c = blockIdx.x * CH + (threadIdx.x >> 5);
+  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < CH && c < C) {
     const float var = r.n > 0.f ? r.m2 / r.n : 0.f;
     const float invstd = rsqrtf(var + eps);
     mean_invstd[c] = r.mean;
@@ -308,16 +317,18 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch
     sh[q] = ss[C + c0 + q];
   }
   // stride is a multiple of groups, so pixel p advances by pstride each iteration; 4 pixels are kept in flight.
+  // Pixels are visited from the END of the tensor (address M-1-p): the producing conv wrote its tiles in ascending
+  // order, so the tail of `x` is what is still in L2 when this kernel starts.
   const long long pstride = stride / groups;
   long long p = idx / groups;
   constexpr int U = 4;
   for (; p + (U - 1) * pstride < M; p += U * pstride) {
     uint4 xv[U], rv[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) xv[u] = *reinterpret_cast<const uint4*>(x + (p + u * pstride) * x_pitch + c0);
+    for (int u = 0; u < U; ++u) xv[u] = *reinterpret_cast<const uint4*>(x + (M - 1 - (p + u * pstride)) * x_pitch + c0);
     if (res) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) rv[u] = *reinterpret_cast<const uint4*>(res + (p + u * pstride) * res_pitch + c0);
+      for (int u = 0; u < U; ++u) rv[u] = *reinterpret_cast<const uint4*>(res + (M - 1 - (p + u * pstride)) * res_pitch + c0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -330,20 +341,21 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch
         if (relu) v = fmaxf(v, 0.f);
         f[q] = v;
       }
-      *reinterpret_cast<uint4*>(y + (p + u * pstride) * y_pitch + c0) = pack8(f);
+      *reinterpret_cast<uint4*>(y + (M - 1 - (p + u * pstride)) * y_pitch + c0) = pack8(f);
     }
   }
   for (; p < M; p += pstride) {
+    const long long pr = M - 1 - p;
     float f[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), f);
-    if (res) unpack8(*reinterpret_cast<const uint4*>(res + p * res_pitch + c0), r);
+    unpack8(*reinterpret_cast<const uint4*>(x + pr * x_pitch + c0), f);
+    if (res) unpack8(*reinterpret_cast<const uint4*>(res + pr * res_pitch + c0), r);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float v = fmaf(f[q], sc[q], sh[q]) + r[q];
       if (relu) v = fmaxf(v, 0.f);
       f[q] = v;
     }
-    *reinterpret_cast<uint4*>(y + p * y_pitch + c0) = pack8(f);
+    *reinterpret_cast<uint4*>(y + pr * y_pitch + c0) = pack8(f);
   }
 }
 
@@ -358,7 +370,9 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
   const int gl = threadIdx.x & 7;
   const int pl = threadIdx.x >> 3;
   const int c0 = blockIdx.x * 64 + gl * 8;
-  const int chunk = blockIdx.y;
+  // blocks are scheduled in ascending blockIdx order: take the chunks from the END of the tensor first (the producer of
+  // dy wrote it in ascending order, so its tail is what L2 still holds); the partial sums keep their chunk index
+  const int chunk = gridDim.y - 1 - blockIdx.y;
   const int r0 = chunk * rows_per_chunk;
   const int r1 = min(M, r0 + rows_per_chunk);
   const bool active = c0 < C;
@@ -671,8 +685,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_p2p_kernel(const float* __re
                                        float* __restrict__ mean_invstd, float* __restrict__ scale_shift, PeerArgs pa) {
   __shared__ Moments sm[32][CH + 1];
   const Moments own_m = block_conv_moments<CH>(part, T, C, blockIdx.x * CH, sm);
-  const int c = blockIdx.x * CH + threadIdx.x;
-  const bool fin = threadIdx.x < CH && c < C;  // this thread finishes channel c
+  const int c = blockIdx.x * CH + (threadIdx.x >> 5);
+  const bool fin = (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < CH && c < C;  // this thread finishes channel c
   const size_t off = static_cast<size_t>(pa.slot) * pa.slot_floats;
   if (fin) {
     float* own = pa.buf[pa.rank] + off;

@@ -84,7 +84,8 @@ ppm_pool_kernel(const __nv_bfloat16* __restrict__ x, int pitch, int N, int H, in
 // dx[n,h,w,c] = sum over bins, over cells whose window contains (h,w): dpooled[n,cell,c] / window_size.
 // One warp per pixel: the (cell, 1/window) list of the pixel is derived once, then the lanes sweep the channels.
 __global__ void __launch_bounds__(256)
-ppm_pool_bwd_kernel(__nv_bfloat16* __restrict__ dx, int pitch, int N, int H, int W, int C, BinSet bs) {
+ppm_pool_bwd_kernel(__nv_bfloat16* __restrict__ dx, int pitch, const __nv_bfloat16* __restrict__ add, int add_pitch, int N,
+                    int H, int W, int C, BinSet bs) {
   const int lane = threadIdx.x & 31;
   const long long npix = static_cast<long long>(N) * H * W;
   const int groups = C >> 3;
@@ -118,6 +119,7 @@ ppm_pool_bwd_kernel(__nv_bfloat16* __restrict__ dx, int pitch, int N, int H, int
     }
     for (int g = lane; g < groups; g += 32) {
       float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (add) ld8(add + p * add_pitch + g * 8, acc);  // the other gradient branch of x (identity part of the concat)
       for (int i = 0; i < cnt; ++i) {
         float f[8];
         ld8(src[i] + g * 8, f);
@@ -265,14 +267,16 @@ extern "C" int semseg_ppm_pool(const void* x, int x_pitch, int N, int H, int W, 
 }
 
 extern "C" int semseg_ppm_pool_bwd(void* const* dpooled, const int* bins, int nb, int N, int H, int W, int C, void* dx,
-                                   int dx_pitch, void* stream_) {
+                                   int dx_pitch, const void* add, int add_pitch, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && dx_pitch % 8 == 0, "ppm_pool_bwd: bad args");
+  SB_CHECK_ARG(!add || (add_pitch % 8 == 0 && add_pitch >= C), "ppm_pool_bwd: bad add pitch %d", add_pitch);
   BinSet bs;
   int r = make_binset(bins, dpooled, nb, &bs);
   if (r) return r;
   const long long warps = static_cast<long long>(N) * H * W;
-  ppm_pool_bwd_kernel<<<ew_blocks(warps * 32), 256, 0, stream>>>(static_cast<bf16*>(dx), dx_pitch, N, H, W, C, bs);
+  ppm_pool_bwd_kernel<<<ew_blocks(warps * 32), 256, 0, stream>>>(static_cast<bf16*>(dx), dx_pitch,
+                                                                 static_cast<const bf16*>(add), add_pitch, N, H, W, C, bs);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }

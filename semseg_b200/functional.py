@@ -406,26 +406,42 @@ def upsample_ce(logits, target, ignore_index):
 
 
 # ------------------------------------------------------------------------------------------------ pyramid pooling
+class _PPMLink:
+    """Carries the identity-branch gradient of x from the concat node to the pooling node of one PPM invocation.
+
+    x feeds both AdaptiveAvgPool (all bins) and the concat (model/pspnet.py:20-26); autograd would add the two gradients
+    with a strided ATen kernel (one of them is a channel slice of the 4096-wide concat gradient). The concat node always
+    runs first in backward (the pooled branch reaches x only through it), so it parks its slice here and returns no
+    gradient for x; the pooling node's kernel adds the slice while it writes dx."""
+    __slots__ = ("dx_identity",)
+
+    def __init__(self):
+        self.dx_identity = None
+
+
 class _PPMPool(torch.autograd.Function):
     """AdaptiveAvgPool2d of every bin in one launch (model/pspnet.py:14)."""
 
     @staticmethod
-    def forward(ctx, x, bins):
-        ctx.bins, ctx.shape = bins, tuple(x.shape)
+    def forward(ctx, x, bins, link):
+        ctx.bins, ctx.shape, ctx.link = bins, tuple(x.shape), link
         return tuple(ops.ppm_pool(x, bins))
 
     @staticmethod
     def backward(ctx, *dpooled):
         n, h, w, c = ctx.shape
-        return ops.ppm_pool_bwd(list(dpooled), ctx.bins, n, h, w, c), None
+        add = None
+        if ctx.link is not None:
+            add, ctx.link.dx_identity = ctx.link.dx_identity, None
+        return ops.ppm_pool_bwd(list(dpooled), ctx.bins, n, h, w, c, add=add), None, None
 
 
 class _PPMUpsampleConcat(torch.autograd.Function):
     """cat([x, bilinear(f_1), ..., bilinear(f_nb)], channel) written in place (model/pspnet.py:25-26)."""
 
     @staticmethod
-    def forward(ctx, x, bins, *feats):
-        ctx.bins, ctx.c, ctx.cr = bins, x.shape[-1], feats[0].shape[-1]
+    def forward(ctx, x, bins, link, *feats):
+        ctx.bins, ctx.c, ctx.cr, ctx.link = bins, x.shape[-1], feats[0].shape[-1], link
         return ops.ppm_upsample_concat(x, list(feats), bins)
 
     @staticmethod
@@ -433,15 +449,23 @@ class _PPMUpsampleConcat(torch.autograd.Function):
         if not dout.is_contiguous():
             dout = dout.contiguous()
         dfeats = ops.ppm_upsample_bwd(dout, ctx.c, ctx.bins, ctx.cr)
-        return (dout[..., :ctx.c], None) + tuple(dfeats)
+        dx = dout[..., :ctx.c]
+        if ctx.link is not None and ctx.needs_input_grad[0] and all(ctx.needs_input_grad[3:]):
+            ctx.link.dx_identity = dx      # summed into dx by the pooling node's kernel (see _PPMLink)
+            dx = None
+        return (dx, None, None) + tuple(dfeats)
 
 
-def ppm_pool(x, bins):
-    return _PPMPool.apply(x, tuple(bins))
+def ppm_pool(x, bins, link=None):
+    return _PPMPool.apply(x, tuple(bins), link)
 
 
-def ppm_upsample_concat(x, feats, bins):
-    return _PPMUpsampleConcat.apply(x, tuple(bins), *feats)
+def ppm_upsample_concat(x, feats, bins, link=None):
+    return _PPMUpsampleConcat.apply(x, tuple(bins), link, *feats)
+
+
+def ppm_link():
+    return _PPMLink()
 
 
 # ------------------------------------------------------------------------------------------------ misc NHWC ops

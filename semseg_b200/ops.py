@@ -454,12 +454,15 @@ def ppm_pool(x, bins):
     return outs
 
 
-def ppm_pool_bwd(dpooled, bins, n, h, w, c):
+def ppm_pool_bwd(dpooled, bins, n, h, w, c, add=None):
+    """dx of ppm_pool; `add` (NHWC bf16, possibly a channel slice of a wider tensor) is summed in."""
     lib = _lib.load()
     dpooled = [d.contiguous() for d in dpooled]
     dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dpooled[0].device)
     barr, parr, nb = _bin_args(bins, dpooled)
-    _lib.check(lib.semseg_ppm_pool_bwd(parr, barr, nb, n, h, w, c, _ptr(dx), c, _stream()), "semseg_ppm_pool_bwd")
+    ap = _nhwc_meta(add)[4] if add is not None else 0
+    _lib.check(lib.semseg_ppm_pool_bwd(parr, barr, nb, n, h, w, c, _ptr(dx), c, _ptr(add), ap, _stream()),
+               "semseg_ppm_pool_bwd")
     return dx
 
 

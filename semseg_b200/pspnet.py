@@ -32,9 +32,10 @@ class PPM(nn.Module):
         for f in self.features:
             b = f[0].output_size
             bins.append(b if isinstance(b, int) else b[0])
-        pooled = SF.ppm_pool(x, bins)                      # one launch: every bin's AdaptiveAvgPool2d
+        link = SF.ppm_link()                                     # the two gradients of x are summed in the pool-bwd kernel
+        pooled = SF.ppm_pool(x, bins, link)                      # one launch: every bin's AdaptiveAvgPool2d
         feats = [SF.conv_bn_act(p, f[1], f[2], relu=True) for p, f in zip(pooled, self.features)]
-        return SF.ppm_upsample_concat(x, feats, bins)      # one launch: upsample x4 + concat, written in place
+        return SF.ppm_upsample_concat(x, feats, bins, link)      # one launch: upsample x4 + concat, written in place
 
     def forward(self, x):
         y = self.forward_nhwc(SF.to_nhwc_bf16(x))

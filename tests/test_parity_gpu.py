@@ -299,6 +299,54 @@ def test_ppm_kernels_vs_torch(shape):
         assert util.rel_l2(f.grad, r.grad.permute(0, 2, 3, 1)) < 6e-3
 
 
+def test_ppm_module_gradient_fan_in_vs_torch():
+    """PPM module (pool -> 1x1 conv + BN + ReLU per bin -> upsample + concat): the gradient of x arrives through the
+    identity part of the concat AND through every pooled branch; here the two are summed inside the pool-backward
+    kernel (functional._PPMLink). Reference: the same computation in fp32 torch on the same weights. The two terms
+    are checked separately (output gradients restricted to the pooled / identity channels) and together."""
+    import copy
+    from semseg_b200.pspnet import PPM
+    torch.manual_seed(3)
+    n, h, w, c, cr, bins = 6, 24, 24, 64, 16, (1, 2, 3, 6)
+    ppm = PPM(c, cr, bins).cuda().train()
+    ref = copy.deepcopy(ppm).float()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((n, h, w, c), device="cuda", generator=g).to(torch.bfloat16)
+    go_full = torch.randn((n, h, w, c + len(bins) * cr), device="cuda", generator=g).to(torch.bfloat16)
+
+    def ours(go):
+        xa = x.clone().requires_grad_(True)
+        out = ppm.forward_nhwc(xa)
+        out.backward(go)
+        return out, xa.grad
+
+    def theirs(go):
+        xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+        feats = [xr]
+        for f in ref.features:
+            y = F.adaptive_avg_pool2d(xr, f[0].output_size)
+            y = torch.relu(F.batch_norm(F.conv2d(y, f[1].weight), None, None, f[2].weight, f[2].bias, True, 0.1,
+                                        f[2].eps))
+            feats.append(F.interpolate(y, (h, w), mode="bilinear", align_corners=True))
+        out = torch.cat(feats, 1)
+        out.backward(go.float().permute(0, 3, 1, 2))
+        return out.permute(0, 2, 3, 1), xr.grad.permute(0, 2, 3, 1)
+
+    go_pool = go_full.clone()
+    go_pool[..., :c] = 0                 # only the pooled branches carry gradient
+    go_id = torch.zeros_like(go_full)
+    go_id[..., :c] = go_full[..., :c]    # only the identity part carries gradient
+    out, dx_pool = ours(go_pool)
+    out_ref, dx_pool_ref = theirs(go_pool)
+    assert util.rel_l2(out, out_ref) < 2e-2
+    assert float(dx_pool.float().abs().max()) > 0 and util.rel_l2(dx_pool, dx_pool_ref) < 5e-2
+    _, dx_id = ours(go_id)
+    assert torch.equal(dx_id, go_id[..., :c])
+    _, dx = ours(go_full)
+    _, dx_ref = theirs(go_full)
+    assert util.rel_l2(dx, dx_ref) < 1e-2
+
+
 def test_maxpool_vs_torch_with_ties():
     """3x3/s2/p1 max-pool; inputs are post-ReLU (many exact ties at 0) so the arg-max tie rule is exercised."""
     from semseg_b200 import functional as SF
