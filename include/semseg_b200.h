@@ -134,6 +134,21 @@ int semseg_wgrad_reduce(const float* dw_partial, int n_splits, int taps, int Cou
 int semseg_pack_weights(const float* w_oihw, int Cout, int Cin, int taps, void* wf, int rows_f, int cols_f,
                         void* wd, int rows_d, int cols_d, void* stream);
 
+/* The same packing for every conv of a model in one launch (torch re-packs after each optimizer step; 2 x 63 small
+ * launches per step for PSPNet50 otherwise). `items` is an array in DEVICE memory, sorted by tile0; an item's tiles are
+ * its 32 x 32 (co, ci) blocks: tiles_ci = ceil(cols_f / 32) per row of ceil(cols_d / 32) rows. wf is
+ * [taps][Cout][cols_f], wd is [taps][Cin][cols_d] (cols_* = Cin / Cout rounded up to 8, zero padded); either may be NULL. */
+typedef struct semseg_pack_item {
+  const float* w;
+  void* wf;
+  void* wd;
+  int Cout, Cin, taps;
+  int cols_f, cols_d;
+  int tile0, tiles_ci;
+  int reserved;
+} semseg_pack_item;
+int semseg_pack_weights_multi(const semseg_pack_item* items_dev, int n_items, int n_tiles, int max_taps, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Layout conversion at the module boundary.
  */

@@ -20,6 +20,17 @@ c_ll = ctypes.c_longlong
 I9 = c_i32 * MAX_TAPS
 
 
+class PackItem(ctypes.Structure):
+    """struct semseg_pack_item (include/semseg_b200.h)."""
+    _fields_ = [
+        ("w", c_vp), ("wf", c_vp), ("wd", c_vp),
+        ("Cout", c_i32), ("Cin", c_i32), ("taps", c_i32),
+        ("cols_f", c_i32), ("cols_d", c_i32),
+        ("tile0", c_i32), ("tiles_ci", c_i32),
+        ("reserved", c_i32),
+    ]
+
+
 class ConvDesc(ctypes.Structure):
     """struct semseg_conv_desc (include/semseg_b200.h)."""
     _fields_ = [
@@ -71,6 +82,7 @@ SIGNATURES = {
     "semseg_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_vp]),
     "semseg_wgrad_reduce": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "semseg_pack_weights": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp]),
+    "semseg_pack_weights_multi": (c_int, [c_vp, c_int, c_int, c_int, c_vp]),
     "semseg_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_nhwc_f32_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

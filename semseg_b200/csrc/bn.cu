@@ -317,18 +317,16 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch
     sh[q] = ss[C + c0 + q];
   }
   // stride is a multiple of groups, so pixel p advances by pstride each iteration; 4 pixels are kept in flight.
-  // Pixels are visited from the END of the tensor (address M-1-p): the producing conv wrote its tiles in ascending
-  // order, so the tail of `x` is what is still in L2 when this kernel starts.
   const long long pstride = stride / groups;
   long long p = idx / groups;
   constexpr int U = 4;
   for (; p + (U - 1) * pstride < M; p += U * pstride) {
     uint4 xv[U], rv[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) xv[u] = *reinterpret_cast<const uint4*>(x + (M - 1 - (p + u * pstride)) * x_pitch + c0);
+    for (int u = 0; u < U; ++u) xv[u] = *reinterpret_cast<const uint4*>(x + (p + u * pstride) * x_pitch + c0);
     if (res) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) rv[u] = *reinterpret_cast<const uint4*>(res + (M - 1 - (p + u * pstride)) * res_pitch + c0);
+      for (int u = 0; u < U; ++u) rv[u] = *reinterpret_cast<const uint4*>(res + (p + u * pstride) * res_pitch + c0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -341,21 +339,20 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch
         if (relu) v = fmaxf(v, 0.f);
         f[q] = v;
       }
-      *reinterpret_cast<uint4*>(y + (M - 1 - (p + u * pstride)) * y_pitch + c0) = pack8(f);
+      *reinterpret_cast<uint4*>(y + (p + u * pstride) * y_pitch + c0) = pack8(f);
     }
   }
   for (; p < M; p += pstride) {
-    const long long pr = M - 1 - p;
     float f[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unpack8(*reinterpret_cast<const uint4*>(x + pr * x_pitch + c0), f);
-    if (res) unpack8(*reinterpret_cast<const uint4*>(res + pr * res_pitch + c0), r);
+    unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), f);
+    if (res) unpack8(*reinterpret_cast<const uint4*>(res + p * res_pitch + c0), r);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float v = fmaf(f[q], sc[q], sh[q]) + r[q];
       if (relu) v = fmaxf(v, 0.f);
       f[q] = v;
     }
-    *reinterpret_cast<uint4*>(y + pr * y_pitch + c0) = pack8(f);
+    *reinterpret_cast<uint4*>(y + p * y_pitch + c0) = pack8(f);
   }
 }
 
@@ -370,9 +367,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
   const int gl = threadIdx.x & 7;
   const int pl = threadIdx.x >> 3;
   const int c0 = blockIdx.x * 64 + gl * 8;
-  // blocks are scheduled in ascending blockIdx order: take the chunks from the END of the tensor first (the producer of
-  // dy wrote it in ascending order, so its tail is what L2 still holds); the partial sums keep their chunk index
-  const int chunk = gridDim.y - 1 - blockIdx.y;
+  const int chunk = blockIdx.y;
   const int r0 = chunk * rows_per_chunk;
   const int r1 = min(M, r0 + rows_per_chunk);
   const bool active = c0 < C;

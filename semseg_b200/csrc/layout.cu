@@ -77,6 +77,56 @@ __global__ void pack_wd_kernel(const float* __restrict__ w, int Cout, int Cin, i
   }
 }
 
+// All conv weights of a model in ONE launch (the per-layer kernels above are launch-latency bound: 2 x 63 launches of
+// 2-3 us per step for PSPNet50). A block owns one 32 (co) x 32 (ci) tile of one layer with all of its taps: the fp32
+// OIHW rows are read once (32*taps contiguous floats per output channel), parked in shared memory, and written out as
+// both bf16 operand slabs (wf[t][co][ci] and wd[t][ci][co], zero padded to the slab widths). items[] lives in device
+// memory and is sorted by tile0; the block finds its layer by binary search.
+__global__ void __launch_bounds__(256) pack_multi_kernel(const semseg_pack_item* __restrict__ items, int n_items) {
+  extern __shared__ float pk_tile[];  // [32][32 * taps + 1]
+  __shared__ int s_item;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_items - 1;
+    const int b = static_cast<int>(blockIdx.x);
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (items[mid].tile0 <= b) lo = mid; else hi = mid - 1;
+    }
+    s_item = lo;
+  }
+  __syncthreads();
+  const semseg_pack_item it = items[s_item];
+  const int lt = static_cast<int>(blockIdx.x) - it.tile0;
+  const int co0 = (lt / it.tiles_ci) * 32, ci0 = (lt % it.tiles_ci) * 32;
+  const int taps = it.taps, rowlen = 32 * taps, pitch = rowlen + 1;
+  const int nci = max(0, min(32, it.Cin - ci0)), nco = max(0, min(32, it.Cout - co0));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < 32; r += 8) {
+    const float* src = it.w + (static_cast<size_t>(co0 + r) * it.Cin + ci0) * taps;
+    for (int e = lane; e < rowlen; e += 32) pk_tile[r * pitch + e] = (r < nco && e < nci * taps) ? src[e] : 0.f;
+  }
+  __syncthreads();
+  const int total = taps * 1024;
+  if (it.wf) {
+    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(it.wf);
+    for (int idx = threadIdx.x; idx < total; idx += 256) {
+      const int ci_l = idx & 31, co_l = (idx >> 5) & 31, t = idx >> 10;
+      if (co_l < nco && ci0 + ci_l < it.cols_f)
+        wf[(static_cast<size_t>(t) * it.Cout + co0 + co_l) * it.cols_f + ci0 + ci_l] =
+            __float2bfloat16_rn(pk_tile[co_l * pitch + ci_l * taps + t]);
+    }
+  }
+  if (it.wd) {
+    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(it.wd);
+    for (int idx = threadIdx.x; idx < total; idx += 256) {
+      const int co_l = idx & 31, ci_l = (idx >> 5) & 31, t = idx >> 10;
+      if (ci_l < nci && co0 + co_l < it.cols_d)
+        wd[(static_cast<size_t>(t) * it.Cin + ci0 + ci_l) * it.cols_d + co0 + co_l] =
+            __float2bfloat16_rn(pk_tile[co_l * pitch + ci_l * taps + t]);
+    }
+  }
+}
+
 // Stride-2 convolutions run on the stride-1 tensor-core kernel through a 2x2 phase decomposition:
 //   xp[(ph*2+pw)*N + n][i][j][c] = x[n][2i+ph][2j+pw][c]   (zero where 2i+ph >= H or 2j+pw >= W)
 // so tap (r, s) of a stride-2 conv reads phase ((r+1)&1, (s+1)&1) at a shift of -1 or 0.
@@ -174,6 +224,17 @@ extern "C" int semseg_pack_weights(const float* w_oihw, int Cout, int Cin, int t
     pack_wd_kernel<<<grid, dim3(32, 8), 0, stream>>>(w_oihw, Cout, Cin, taps, static_cast<bf16*>(wd), rows_d, cols_d);
     SB_LAUNCHED();
   }
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_pack_weights_multi(const semseg_pack_item* items_dev, int n_items, int n_tiles, int max_taps,
+                                         void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(items_dev && n_items > 0 && n_tiles > 0 && max_taps > 0 && max_taps <= SEMSEG_MAX_TAPS,
+               "pack_weights_multi: bad args");
+  const size_t smem = static_cast<size_t>(32) * (32 * max_taps + 1) * sizeof(float);
+  sb::pack_multi_kernel<<<static_cast<unsigned>(n_tiles), 256, smem, stream>>>(items_dev, n_items);
+  SB_LAUNCHED();
   return SEMSEG_OK;
 }
 

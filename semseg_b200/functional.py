@@ -34,6 +34,27 @@ def packed(conv, need_dgrad=True):
     return pw
 
 
+def prepack(model):
+    """Refresh the operand slabs of every native conv of `model` in one launch when its weights changed (call at the top
+    of a training forward). Convs keep working without it: `packed` falls back to the per-layer kernels."""
+    convs = [m for m in model.modules() if isinstance(m, nn.Conv2d) and m.weight.is_cuda and
+             m.weight.dtype == torch.float32 and m.weight.is_contiguous() and m.kernel_size[0] == m.kernel_size[1] and
+             m.kernel_size[0] * m.kernel_size[1] <= ops.MAX_TAPS]
+    if not convs:
+        return
+    keys = [(c.weight._version, c.weight.data_ptr(), True) for c in convs]
+    if all(c.__dict__.get("_sb_pack", (None,))[0] == k for c, k in zip(convs, keys)):
+        return                                            # nothing changed since the last pack
+    plan = model.__dict__.get("_sb_pack_plan")
+    weights = [c.weight.detach() for c in convs]
+    if plan is None or not plan.valid_for(weights):
+        plan = ops.WeightPackPlan(weights)
+        model.__dict__["_sb_pack_plan"] = plan
+    plan.refresh()
+    for c, k, pw in zip(convs, keys, plan.packs):
+        c.__dict__["_sb_pack"] = (k, pw)
+
+
 def _sync_group(bn):
     """Process group when `bn` is a SyncBatchNorm that must synchronise, else None."""
     if isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized():

@@ -89,6 +89,49 @@ def pack_weights(w, need_dgrad=True):
     return PackedWeight(wf, wd, cout, cin, taps, kh)
 
 
+class WeightPackPlan:
+    """Persistent bf16 operand slabs for a list of conv weights, refreshed in ONE launch (semseg_pack_weights_multi).
+
+    The fp32 OIHW parameters stay the masters (optimizer / DDP / checkpoints); after an optimizer step every conv of the
+    model needs new slabs, which costs 2 launches per conv on the per-layer path. The plan owns one (wf, wd) pair per
+    conv and a device-side item table; `refresh()` re-packs all of them into the same buffers."""
+
+    def __init__(self, weights):
+        import ctypes
+        _require_cuda(*weights)
+        self.weights = [w for w in weights]
+        self.ptrs = [w.data_ptr() for w in weights]
+        self.packs = []
+        items = (_lib.PackItem * len(weights))()
+        tile0, max_taps = 0, 1
+        for k, w in enumerate(weights):
+            assert w.dtype == torch.float32 and w.dim() == 4 and w.is_contiguous() and w.shape[2] == w.shape[3]
+            cout, cin, kh, _ = w.shape
+            taps = kh * kh
+            assert taps <= MAX_TAPS
+            cin_p, cout_p = round_up(cin, 8), round_up(cout, 8)
+            wf = torch.empty((taps, cout, cin_p), dtype=torch.bfloat16, device=w.device)
+            wd = torch.empty((taps, cin, cout_p), dtype=torch.bfloat16, device=w.device)
+            self.packs.append(PackedWeight(wf, wd, cout, cin, taps, kh))
+            it = items[k]
+            it.w, it.wf, it.wd = w.data_ptr(), wf.data_ptr(), wd.data_ptr()
+            it.Cout, it.Cin, it.taps, it.cols_f, it.cols_d = cout, cin, taps, cin_p, cout_p
+            it.tile0, it.tiles_ci = tile0, (cin_p + 31) // 32
+            tile0 += it.tiles_ci * ((cout_p + 31) // 32)
+            max_taps = max(max_taps, taps)
+        self.n_items, self.n_tiles, self.max_taps = len(weights), tile0, max_taps
+        raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8)
+        self.items_dev = raw.to(weights[0].device)
+
+    def valid_for(self, weights):
+        return len(weights) == len(self.ptrs) and all(w.data_ptr() == p for w, p in zip(weights, self.ptrs))
+
+    def refresh(self):
+        lib = _lib.load()
+        _lib.check(lib.semseg_pack_weights_multi(_ptr(self.items_dev), self.n_items, self.n_tiles, self.max_taps,
+                                                 _stream()), "semseg_pack_weights_multi")
+
+
 def conv_taps(ksize, dilation, transpose=False):
     """[(dh, dw, wtap)] of a stride-1 'same' conv; transpose=True gives the dgrad taps."""
     taps = []

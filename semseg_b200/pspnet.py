@@ -116,6 +116,8 @@ class PSPNet(nn.Module):
         h = int((x_size[2] - 1) / 8 * self.zoom_factor + 1)
         w = int((x_size[3] - 1) / 8 * self.zoom_factor + 1)
 
+        if self.training and torch.is_grad_enabled():
+            SF.prepack(self)      # all conv operand slabs refreshed in one launch after an optimizer step
         t = SF.to_nhwc_bf16(x)
         t = self.layer0.forward_nhwc(t)
         t = self.layer1.forward_nhwc(t)

@@ -173,6 +173,27 @@ def test_conv_epilogues():
     assert bool((buf[..., :256] == 0).all())
 
 
+def test_pack_weights_multi_matches_per_layer_pack():
+    """One-launch packing of a whole list of conv weights == the per-layer kernels, bit for bit (incl. zero padding of
+    Cin = 3 -> 8 and Cout = 150 -> 152), and again after an in-place update of the masters."""
+    from semseg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shapes = [(64, 3, 3), (64, 64, 3), (256, 64, 1), (150, 512, 1), (512, 4096, 3), (40, 24, 3), (2048, 512, 1)]
+    ws = [torch.randn((co, ci, k, k), device="cuda", generator=g) for co, ci, k in shapes]
+    plan = ops.WeightPackPlan(ws)
+    for rnd in range(2):
+        for pk in plan.packs:                      # poison: every element must be rewritten
+            pk.wf.fill_(7.0)
+            pk.wd.fill_(7.0)
+        plan.refresh()
+        for w, pk in zip(ws, plan.packs):
+            ref = ops.pack_weights(w)
+            assert torch.equal(pk.wf, ref.wf) and torch.equal(pk.wd, ref.wd), tuple(w.shape)
+        for w in ws:
+            w.mul_(0.5).add_(0.01)
+    assert plan.valid_for(ws) and not plan.valid_for(ws[:-1])
+
+
 def test_bn_kernels_vs_torch():
     from semseg_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(3)
