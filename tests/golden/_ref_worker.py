@@ -77,8 +77,78 @@ def golden_psamask():
     print("psamask goldens written")
 
 
+class TinySegNet(torch.nn.Module):
+    """Deterministic stand-in network for the sliding-window goldens (weights from a seeded generator, independent of
+    nn init order). stride = 1: logits at the input size; stride = 8: logits at 1/8 size (the caller resizes)."""
+
+    def __init__(self, classes=5, stride=1, seed=5):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.weight = torch.nn.Parameter(torch.randn((classes, 3, 3, 3), generator=g) * 0.6)
+        self.bias = torch.nn.Parameter(torch.randn((classes,), generator=g) * 0.1)
+        self.stride = stride
+
+    def forward(self, x):
+        if self.stride > 1:
+            x = torch.nn.functional.avg_pool2d(x, self.stride)
+        return torch.nn.functional.conv2d(x, self.weight, self.bias, padding=1)
+
+
+SW_CFG = dict(classes=5, base_size=64, crop_h=33, crop_w=33, scales=[0.75, 1.0, 1.5],
+              mean=[0.485 * 255, 0.456 * 255, 0.406 * 255], std=[0.229 * 255, 0.224 * 255, 0.225 * 255])
+
+
+def sw_image(seed=9, h=40, w=60):
+    rng = np.random.default_rng(seed)
+    return (rng.random((h, w, 3)) * 255).astype(np.float32)
+
+
+def golden_sliding_window():
+    """Outputs of the reference's own net_process / scale_process and of its evaluation-loop body (tool/test.py:122-199)
+    for two tiny deterministic networks. `.cuda()` is made a no-op (this container has no GPU); nothing else is shimmed."""
+    import importlib.util
+    import cv2
+    spec = importlib.util.spec_from_file_location("ref_tool_test", os.path.join(os.getcwd(), "tool", "test.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    c = SW_CFG
+    image = sw_image()
+    h, w, _ = image.shape
+    res = {"image": image}
+    for tag, stride in (("s1", 1), ("s8", 8)):
+        model = TinySegNet(c["classes"], stride).eval()
+        res[tag + "/net_process"] = ref.net_process(model, image[:33, :33].copy(), c["mean"], c["std"])
+        res[tag + "/net_process_nostd_noflip"] = ref.net_process(model, image[3:36, 7:40].copy(), c["mean"], None, flip=False)
+        res[tag + "/scale_process"] = ref.scale_process(model, image, c["classes"], c["crop_h"], c["crop_w"], h, w,
+                                                        c["mean"], c["std"])
+        # body of the evaluation loop, tool/test.py:186-199
+        prediction = np.zeros((h, w, c["classes"]), dtype=float)
+        for scale in c["scales"]:
+            long_size = round(scale * c["base_size"])
+            new_h = long_size
+            new_w = long_size
+            if h > w:
+                new_w = round(long_size / float(h) * w)
+            else:
+                new_h = round(long_size / float(w) * h)
+            image_scale = cv2.resize(image, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
+            prediction += ref.scale_process(model, image_scale, c["classes"], c["crop_h"], c["crop_w"], h, w,
+                                            c["mean"], c["std"])
+        prediction /= len(c["scales"])
+        res[tag + "/scores"] = prediction
+        res[tag + "/argmax"] = np.argmax(prediction, axis=2).astype(np.int16)
+    np.savez_compressed(os.path.join(OUT, "sliding_window.npz"), **res)
+    print("sliding-window goldens written")
+
+
 def main():
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "sliding":
+        golden_sliding_window()
+        return
     golden_psamask()
+    golden_sliding_window()
 
     from model.pspnet import PSPNet
     from model.psanet import PSANet

@@ -1,7 +1,8 @@
 """Generate the golden fixtures in tests/golden/ from the REAL reference (hszhao/semseg at /root/reference).
 
 Run once in the build container (the reference does not exist on the GPU box):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # everything (minutes: three full networks on CPU)
+    python tests/golden/make_golden.py sliding    # only the sliding-window inference fixtures
 It copies the reference to a scratch dir (lib/psa JIT-builds in place), then runs `_ref_worker` in a
 subprocess whose PYTHONPATH contains ONLY the reference copy, so `model.pspnet` / `lib.psa.functional` are the
 reference's own modules (this repository ships packages with the same names).
@@ -25,7 +26,7 @@ def main():
     env = dict(os.environ)
     env["PYTHONPATH"] = SCRATCH
     env["GOLDEN_OUT"] = HERE
-    subprocess.check_call([sys.executable, os.path.join(HERE, "_ref_worker.py")], cwd=SCRATCH, env=env)
+    subprocess.check_call([sys.executable, os.path.join(HERE, "_ref_worker.py")] + sys.argv[1:], cwd=SCRATCH, env=env)
 
 
 if __name__ == "__main__":

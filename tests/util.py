@@ -40,3 +40,28 @@ def oracle_from(model, arch, **kw):
         if k in params:
             v.requires_grad_(True)
     return Oracle(sd, arch=arch, **kw), sd
+
+
+class TinySegNet(torch.nn.Module):
+    """Deterministic stand-in network of the sliding-window goldens (identical to tests/golden/_ref_worker.py)."""
+
+    def __init__(self, classes=5, stride=1, seed=5):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.weight = torch.nn.Parameter(torch.randn((classes, 3, 3, 3), generator=g) * 0.6)
+        self.bias = torch.nn.Parameter(torch.randn((classes,), generator=g) * 0.1)
+        self.stride = stride
+
+    def forward(self, x):
+        if self.stride > 1:
+            x = torch.nn.functional.avg_pool2d(x, self.stride)
+        return torch.nn.functional.conv2d(x, self.weight, self.bias, padding=1)
+
+
+SW_CFG = dict(classes=5, base_size=64, crop_h=33, crop_w=33, scales=[0.75, 1.0, 1.5],
+              mean=[0.485 * 255, 0.456 * 255, 0.406 * 255], std=[0.229 * 255, 0.224 * 255, 0.225 * 255])
+
+
+def sw_image(seed=9, h=40, w=60):
+    rng = np.random.default_rng(seed)
+    return (rng.random((h, w, 3)) * 255).astype(np.float32)

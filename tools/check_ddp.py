@@ -88,7 +88,9 @@ def block_checks(rank, world, dev):
             e_p = max(rel(a.grad, b.grad) for a, b in zip(sync.parameters(), single.parameters()))
             bs, b1 = dict(sync.named_buffers()), dict(single.named_buffers())
             e_b = max(rel(bs[k], b1[k]) for k in b1 if "running" in k)
-            good = e_y < 2e-3 and e_dx < 2e-2 and e_p < 2e-2 and e_b < 1e-5
+            # running stats of the later BNs inherit the bf16-ulp flips of the earlier activations (e_y ~ 1e-4):
+            # ~1e-5 rel-L2 is that noise, a statistics bug would show up at 1e-2 and above
+            good = e_y < 2e-3 and e_dx < 2e-2 and e_p < 2e-2 and e_b < 1e-4
             print("%-28s y %.2e  dx %.2e  dparam %.2e  running %.2e  %s" % (name, e_y, e_dx, e_p, e_b,
                                                                          "OK" if good else "FAIL"), flush=True)
             ok &= good
