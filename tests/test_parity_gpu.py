@@ -581,3 +581,30 @@ def test_state_dict_round_trip_with_oracle_weights():
     m.eval(), m2.eval()
     with torch.no_grad():
         assert torch.equal(m(x), m2(x))        # deterministic kernels: same weights, same bits
+
+
+# ------------------------------------------------------------------------------------------------ sliding-window inference
+def test_sliding_window_engine_bit_identical_to_serial_oracle():
+    """the batched engine (all crops of a scale per forward call, device-side flip / softmax /
+    accumulate) against the serial one-crop-at-a-time oracle, both driving the same eval-mode PSPNet50 on the GPU.
+    Every tile of the CUDA path belongs to one image, so the per-crop scores do not depend on the batch and the two
+    procedures must agree bit for bit."""
+    from oracle import sliding_window as osw
+    from semseg_b200 import inference
+    c = util.SW_CFG
+    classes, crop = 7, 65
+    model = util.build_pspnet(50, classes=classes).cuda().eval()
+    image = util.sw_image(seed=4, h=100, w=150)
+    scales, base = [0.75, 1.0], 150
+    eng = inference.SlidingWindowPredictor(model, classes, crop, crop, c["mean"], c["std"], max_batch=16)
+    scores, amax = eng(image, base, scales)
+    ref_scores, ref_amax = osw.score_image(model, image, classes, c["mean"], c["std"], base, crop, crop, scales)
+    assert scores.shape == (100, 150, classes) and np.isfinite(scores).all()
+    assert np.allclose(scores.sum(2), 1.0, atol=1e-5)              # averages of softmax rows
+    assert np.array_equal(scores, ref_scores)
+    assert np.array_equal(amax, ref_amax)
+    crops = sum(len(inference.crop_origins(max(nh, crop), crop)) * len(inference.crop_origins(max(nw, crop), crop))
+                for nh, nw in (inference.scaled_size(100, 150, round(s * base)) for s in scales))
+    assert eng.forward_calls < crops                                # the reference: one model call per crop
+    one = inference.net_process(model, image[:crop, :crop].copy(), c["mean"], c["std"])
+    assert np.array_equal(one, osw.score_crop(model, image[:crop, :crop].copy(), c["mean"], c["std"]))
