@@ -3,14 +3,19 @@
 The reference (tool/test.py:122-199, mirrored in tool/demo.py:106-181) pushes ONE crop (+ its mirror) through the
 network per call: at base size 2048 / crop 713 / six scales that is 81 crops = 162 serial forward passes and 81
 device→host copies of a [classes, 713, 713] score map per image, with the accumulation done by numpy on the host.
-Here every crop of a scale goes through the network in batches, mirroring / softmax / flip-averaging / accumulation /
-normalisation by the overlap count stay on the device, and one score map per scale crosses PCIe.
-
-Same results: crop grid, padding, normalisation, flip averaging, float64 accumulation order (grid order), division by
-the overlap count, un-padding and the cv2 resizes are the reference's, so for a network whose per-image output does not
-depend on what else is in the batch (true for this package's kernels: every tile belongs to one image) the scores are
-bit-identical to the serial procedure. `net_process` / `scale_process` keep the reference's signatures and return
-types; `SlidingWindowPredictor` is the object form that also covers the per-image scale loop.
+Here every crop of a scale goes through the network in batches and mirroring / softmax / flip-averaging /
+accumulation / normalisation by the overlap count stay on the device. Two ways to finish:
+  * exact=True — each scale's score map goes to the host once and the reference's own last steps (cv2 INTER_LINEAR
+    resize to the image size, numpy sum over scales, argmax) run there. Crop grid, padding, normalisation, flip
+    averaging, float64 accumulation order and the resizes are the reference's, so for a network whose per-image output
+    does not depend on what else is in the batch (true for this package's kernels: every tile belongs to one image) the
+    scores are bit-identical to the serial procedure.
+  * exact=False (default) — the per-scale resize (same half-pixel bilinear sampling as cv2.INTER_LINEAR, fp64 weights),
+    the sum over scales and the argmax also run on the device; only the result crosses PCIe. At 1024x2048 x 19 classes
+    the host steps of the reference procedure (float64 [h, w, classes] arrays through cv2 and numpy) cost several times
+    the network itself. Scores agree with the exact path to ~1e-7.
+`net_process` / `scale_process` keep the reference's signatures and return types (and the exact arithmetic);
+`SlidingWindowPredictor` is the object form that also covers the per-image scale loop.
 
 The engine is device-agnostic torch glue around `model(batch)`; the arithmetic that matters (the network) is the CUDA
 path of this package when `model` is a semseg_b200 PSPNet / PSANet in eval mode.
@@ -89,9 +94,9 @@ class SlidingWindowPredictor:
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     # ------------------------------------------------------------------------------------------- one scale
-    def scale(self, image, out_h, out_w):
-        """Scores float64 [out_h, out_w, classes] of one (already rescaled) float32 HWC image
-        (= scale_process, tool/test.py:148-178)."""
+    def _scale_canvas(self, image):
+        """Overlap-normalised scores of one rescaled image, un-padded: float64 [classes, img_h, img_w] on the device
+        (tool/test.py:148-176: padding, crop grid, accumulation in grid order, division by the crop count)."""
         ch, cw = self.crop_h, self.crop_w
         img_h, img_w = image.shape[:2]
         extra_h, extra_w = max(ch - img_h, 0), max(cw - img_w, 0)
@@ -111,22 +116,43 @@ class SlidingWindowPredictor:
             canvas[:, y0:y0 + ch, x0:x0 + cw] += scores[k]
             hits[y0:y0 + ch, x0:x0 + cw] += 1
         canvas /= torch.from_numpy(hits).to(self.device)
-        canvas = canvas[:, top:top + img_h, left:left + img_w]
-        host = canvas.permute(1, 2, 0).contiguous().cpu().numpy()           # the one device->host copy of this scale
+        return canvas[:, top:top + img_h, left:left + img_w]
+
+    def scale(self, image, out_h, out_w):
+        """Scores float64 [out_h, out_w, classes] of one (already rescaled) float32 HWC image — scale_process,
+        tool/test.py:148-178, with the reference's own final step (cv2 INTER_LINEAR on the host): bit-identical to the
+        serial procedure; one device->host copy per scale."""
+        host = self._scale_canvas(image).permute(1, 2, 0).contiguous().cpu().numpy()
         return cv2.resize(host, (out_w, out_h), interpolation=cv2.INTER_LINEAR)
 
+    def scale_on_device(self, image, out_h, out_w):
+        """Same scores as `scale`, float64 [classes, out_h, out_w], resized on the device (bilinear, half-pixel centres,
+        no anti-aliasing = cv2.INTER_LINEAR's sampling; cv2 rounds its interpolation weights to fp32, so the two agree
+        to ~1e-7, not bit for bit)."""
+        canvas = self._scale_canvas(image)
+        return F.interpolate(canvas[None], size=(out_h, out_w), mode="bilinear", align_corners=False)[0]
+
     # ------------------------------------------------------------------------------------------- one image
-    def __call__(self, image, base_size, scales):
-        """(scores float64 [h, w, classes], argmax int64 [h, w]) of a float32 HWC image: the body of the evaluation
-        loop, tool/test.py:186-199."""
+    def __call__(self, image, base_size, scales, exact=False, return_scores=True):
+        """(scores float64 [h, w, classes] or None, argmax int64 [h, w]) of a float32 HWC image: the body of the
+        evaluation loop, tool/test.py:186-199.
+
+        exact=True  : every step as in the reference (host cv2 resize of each scale's score map, numpy accumulation):
+                      bit-identical to the serial procedure, but the host works on [h, w, classes] float64 arrays.
+        exact=False : score maps are resized, summed over the scales and arg-maxed on the device; only the result
+                      crosses PCIe (the argmax, plus the scores when return_scores)."""
         h, w = image.shape[:2]
-        total = np.zeros((h, w, self.classes), dtype=np.float64)
+        total = np.zeros((h, w, self.classes), dtype=np.float64) if exact else \
+            torch.zeros((self.classes, h, w), dtype=torch.float64, device=self.device)
         for s in scales:
             new_h, new_w = scaled_size(h, w, round(s * base_size))
             resized = cv2.resize(image, (new_w, new_h), interpolation=cv2.INTER_LINEAR)
-            total += self.scale(resized, h, w)
+            total += self.scale(resized, h, w) if exact else self.scale_on_device(resized, h, w)
         total /= len(scales)
-        return total, np.argmax(total, axis=2)
+        if exact:
+            return total, np.argmax(total, axis=2)
+        amax = total.argmax(0).cpu().numpy()
+        return (total.permute(1, 2, 0).contiguous().cpu().numpy() if return_scores else None), amax
 
 
 def net_process(model, image, mean, std=None, flip=True):

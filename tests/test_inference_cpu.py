@@ -48,7 +48,7 @@ def test_batched_engine_matches_serial_oracle(golden, stride, max_batch):
     model = util.TinySegNet(c["classes"], stride).eval()
     eng = inference.SlidingWindowPredictor(model, c["classes"], c["crop_h"], c["crop_w"], c["mean"], c["std"],
                                            max_batch=max_batch)
-    scores, amax = eng(image, c["base_size"], c["scales"])
+    scores, amax = eng(image, c["base_size"], c["scales"], exact=True)
     ref_scores, ref_amax = osw.score_image(model, image, c["classes"], c["mean"], c["std"], c["base_size"],
                                            c["crop_h"], c["crop_w"], c["scales"])
     # a CPU conv may pick another blocking for another batch size: allow fp32 rounding, not more
@@ -66,6 +66,12 @@ def test_batched_engine_matches_serial_oracle(golden, stride, max_batch):
                   len(inference.crop_origins(max(inference.scaled_size(h, w, round(s * c["base_size"]))[1], c["crop_w"]),
                                              c["crop_w"])) / (max_batch // 2)) for s in c["scales"])
     assert eng.forward_calls <= n_crops          # the reference makes one model call per crop
+    # device-side resize / accumulation / argmax: same sampling as cv2.INTER_LINEAR, weights in fp64 instead of fp32
+    fast_scores, fast_amax = eng(image, c["base_size"], c["scales"])
+    assert np.allclose(fast_scores, ref_scores, rtol=0, atol=5e-6)
+    assert (fast_amax != ref_amax).mean() < 1e-3
+    none_scores, amax2 = eng(image, c["base_size"], c["scales"], return_scores=False)
+    assert none_scores is None and np.array_equal(amax2, fast_amax)
 
 
 def test_reference_named_entry_points(golden):

@@ -597,7 +597,7 @@ def test_sliding_window_engine_bit_identical_to_serial_oracle():
     image = util.sw_image(seed=4, h=100, w=150)
     scales, base = [0.75, 1.0], 150
     eng = inference.SlidingWindowPredictor(model, classes, crop, crop, c["mean"], c["std"], max_batch=16)
-    scores, amax = eng(image, base, scales)
+    scores, amax = eng(image, base, scales, exact=True)
     ref_scores, ref_amax = osw.score_image(model, image, classes, c["mean"], c["std"], base, crop, crop, scales)
     assert scores.shape == (100, 150, classes) and np.isfinite(scores).all()
     assert np.allclose(scores.sum(2), 1.0, atol=1e-5)              # averages of softmax rows
@@ -606,5 +606,7 @@ def test_sliding_window_engine_bit_identical_to_serial_oracle():
     crops = sum(len(inference.crop_origins(max(nh, crop), crop)) * len(inference.crop_origins(max(nw, crop), crop))
                 for nh, nw in (inference.scaled_size(100, 150, round(s * base)) for s in scales))
     assert eng.forward_calls < crops                                # the reference: one model call per crop
+    fast_scores, fast_amax = eng(image, base, scales)               # device-side resize / sum over scales / argmax
+    assert np.allclose(fast_scores, ref_scores, rtol=0, atol=5e-6) and (fast_amax != ref_amax).mean() < 1e-3
     one = inference.net_process(model, image[:crop, :crop].copy(), c["mean"], c["std"])
     assert np.array_equal(one, osw.score_crop(model, image[:crop, :crop].copy(), c["mean"], c["std"]))

@@ -9,4 +9,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -f -o gpurun_
   -k regex:"conv_igemm|conv_wgrad|bn_|upsample_ce|psamask|ppm_|wgrad_reduce" python tools/ncu_kernels.py > gpurun_out/ncu_kernels.log 2>&1
 echo "full capture rc=$?"
 ncu -i gpurun_out/prof_kernels.ncu-rep --page raw --csv > gpurun_out/prof_kernels_raw.csv 2>/dev/null
+rm -f gpurun_out/prof_kernels.ncu-rep gpurun_out/prof_n64.ncu-rep   # only the CSV exports travel back (64 MiB cap)
 ls -la gpurun_out/ | head -20

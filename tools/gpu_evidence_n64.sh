@@ -6,4 +6,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -f -o gpurun_
 echo "n64 capture rc=$?"
 ncu -i gpurun_out/prof_n64.ncu-rep --page raw --csv > gpurun_out/prof_n64_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_n64.ncu-rep --page source --csv > gpurun_out/prof_n64_source.csv 2>/dev/null
+rm -f gpurun_out/prof_kernels.ncu-rep gpurun_out/prof_n64.ncu-rep   # only the CSV exports travel back (64 MiB cap)
 ls -la gpurun_out | grep n64
