@@ -159,6 +159,11 @@ int semseg_nhwc_bf16_to_nchw_f32(const void* in, float* out, int N, int C, int H
 int semseg_nhwc_f32_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W, int in_pitch,
                                 void* stream);
 
+/* Stem conv (3x3, stride 2, pad 1, Cin <= 3 — model/resnet.py:106-108) as a 1x1 conv over input patches:
+ *   out[n, ho, wo, (r*3+s)*Cin + c] = x[n, 2ho-1+r, 2wo-1+s, c], zero outside the image and for columns >= 9*Cin;
+ *   out is [N, (H-1)/2+1, (W-1)/2+1, 32] bf16. x is NHWC bf16 with x_pitch >= 4 (the first Cin channels are read). */
+int semseg_im2col3x3s2(const void* x, int x_pitch, int N, int H, int W, int Cin, void* out, void* stream);
+
 /* 2x2 phase decomposition used to run stride-2 convolutions (model/resnet.py:108 conv1, layer2.0 conv2 and
  * downsample) on the stride-1 tensor-core kernel:
  *   xp [4][N][Hh][Wh][C], Hh = (H+1)/2:  xp[ph*2+pw][n][i][j] = x[n][2i+ph][2j+pw] (zero outside x). */

@@ -127,6 +127,42 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const semseg_pack_item*
   }
 }
 
+// Stem conv (3x3, stride 2, pad 1, <= 3 input channels; model/resnet.py:106-108): patches of the input, so the conv
+// becomes ONE 64-wide K block (27 real values) per output pixel instead of 9 taps x 64-wide K blocks that are 7/8 zero
+// fill fetched in 16-byte pieces:  P[n, ho, wo, (r*3+s)*3 + c] = x[n, 2ho-1+r, 2wo-1+s, c]  (zero outside, 27..31 zero).
+__global__ void __launch_bounds__(256) im2col3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int pitch, int N, int H,
+                                                          int W, int Cin, int Ho, int Wo, __nv_bfloat16* __restrict__ out) {
+  const long long total = static_cast<long long>(N) * Ho * Wo;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wo = static_cast<int>(idx % Wo);
+    const int ho = static_cast<int>((idx / Wo) % Ho);
+    const int n = static_cast<int>(idx / (static_cast<long long>(Wo) * Ho));
+    __align__(16) __nv_bfloat16 v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __float2bfloat16_rn(0.f);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hi = 2 * ho - 1 + r;
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) {
+        const int wi = 2 * wo - 1 + sx;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+          const uint2 px = *reinterpret_cast<const uint2*>(x + ((static_cast<size_t>(n) * H + hi) * W + wi) * pitch);
+          const __nv_bfloat16* pc = reinterpret_cast<const __nv_bfloat16*>(&px);   // 4 channels, Cin <= 3 are real
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c < Cin) v[(r * 3 + sx) * Cin + c] = pc[c];
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + idx * 32);
+    const uint4* src = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = src[q];
+  }
+}
+
 // Stride-2 convolutions run on the stride-1 tensor-core kernel through a 2x2 phase decomposition:
 //   xp[(ph*2+pw)*N + n][i][j][c] = x[n][2i+ph][2j+pw][c]   (zero where 2i+ph >= H or 2j+pw >= W)
 // so tap (r, s) of a stride-2 conv reads phase ((r+1)&1, (s+1)&1) at a shift of -1 or 0.
@@ -224,6 +260,21 @@ extern "C" int semseg_pack_weights(const float* w_oihw, int Cout, int Cin, int t
     pack_wd_kernel<<<grid, dim3(32, 8), 0, stream>>>(w_oihw, Cout, Cin, taps, static_cast<bf16*>(wd), rows_d, cols_d);
     SB_LAUNCHED();
   }
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_im2col3x3s2(const void* x, int x_pitch, int N, int H, int W, int Cin, void* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(x && out && N > 0 && H > 0 && W > 0 && Cin >= 1 && Cin <= 3 && x_pitch >= 4 && x_pitch % 4 == 0,
+               "im2col3x3s2: needs 1..3 input channels in a pitch that is a multiple of 4 (got Cin=%d pitch=%d)", Cin,
+               x_pitch);
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = static_cast<long long>(N) * Ho * Wo;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sb::im2col3x3s2_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(x), x_pitch, N, H, W,
+                                                                           Cin, Ho, Wo, static_cast<bf16*>(out));
+  SB_LAUNCHED();
   return SEMSEG_OK;
 }
 

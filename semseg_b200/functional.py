@@ -34,6 +34,28 @@ def packed(conv, need_dgrad=True):
     return pw
 
 
+def packed_patches(conv):
+    """Operand slab of the stem conv in its patch form (ops.im2col3x3s2): wf [1][Cout][32] with column
+    (r*3+s)*Cin + c = weight[:, c, r, s], zero padded; re-made only when the parameter changed."""
+    w = conv.weight
+    key = (w._version, w.data_ptr(), "patches")
+    cache = conv.__dict__.get("_sb_pack_patches")
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    cout, cin = w.shape[0], w.shape[1]
+    flat = w.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    wf = torch.zeros((1, cout, 32), dtype=torch.bfloat16, device=w.device)
+    wf[0, :, :9 * cin] = flat
+    conv.__dict__["_sb_pack_patches"] = (key, wf)
+    return wf
+
+
+def _is_patch_conv(conv, x):
+    """The 3-channel stride-2 stem conv (model/resnet.py:106-108) on an input that needs no gradient."""
+    return (conv.kernel_size == (3, 3) and conv.stride == (2, 2) and conv.dilation == (1, 1) and conv.padding == (1, 1)
+            and conv.in_channels <= 3 and conv.groups == 1 and x.shape[-1] >= 4)
+
+
 def prepack(model):
     """Refresh the operand slabs of every native conv of `model` in one launch when its weights changed (call at the top
     of a training forward). Convs keep working without it: `packed` falls back to the per-layer kernels."""
@@ -117,7 +139,7 @@ class _CbaState:
                  "in_shape", "has_res")
 
 
-def cba_forward(x, conv, bn, relu, residual, out=None):
+def cba_forward(x, conv, bn, relu, residual, out=None, input_needs_grad=True):
     """conv (1x1 / 3x3; stride 1 with any dilation, or stride 2) + training BatchNorm + optional residual + ReLU.
     Returns (y, state). Three launches: conv_fprop (raw + per-CTA statistics) -> finalise (+ SyncBN exchange) -> apply.
 
@@ -127,15 +149,20 @@ def cba_forward(x, conv, bn, relu, residual, out=None):
     pw = packed(conv)
     k, dil, stride = conv.kernel_size[0], conv.dilation[0], conv.stride[0]
     n, h, w, cx = x.shape
+    wf = pw.wf
     if stride == 1:
         xin, img_add, out_nhw = x, None, None
         taps = ops.conv_taps(k, dil)
+    elif not input_needs_grad and _is_patch_conv(conv, x):
+        # stem conv: one 1x1 conv over 27-value input patches instead of 9 taps of a 3(->64)-channel K block
+        xin, img_add, out_nhw = ops.im2col3x3s2(x, conv.in_channels), None, None
+        taps, wf, stride = ops.conv_taps(1, 1), packed_patches(conv), 0       # stride 0 marks the patch form
     else:
         xin = ops.space_to_phases(x)                     # [4N, Hh, Wh, C]
         t2 = ops.conv_taps_s2(k, n)
         taps, img_add = [t[:3] for t in t2], [t[3] for t in t2]
         out_nhw = (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1)
-    raw, sp = ops.conv_fprop(xin, pw.wf, pw.cout, taps, stats=True, img_add=img_add, out_nhw=out_nhw)
+    raw, sp = ops.conv_fprop(xin, wf, pw.cout, taps, stats=True, img_add=img_add, out_nhw=out_nhw)
     pg = _sync_group(bn)
     track = bn.track_running_stats and bn.running_mean is not None
     mom = _bn_momentum(bn) if track else 0.0
@@ -172,6 +199,14 @@ def cba_backward(st, dy, need_dx=True, need_dw=True, need_dres=False, dx_add=Non
     d_raw, dres, dgamma, dbeta = _bn_backward(st.pg, st.world, dy, st.y, st.raw, st.mi, st.gamma, st.relu,
                                               st.has_res and need_dres, st.ss)
     dx = dw = None
+    if st.stride == 0:      # patch form of the stem conv (no input gradient by construction)
+        if need_dx:
+            raise RuntimeError("semseg_b200: the patch form of the stem conv was chosen but dx is requested")
+        if need_dw:
+            cin = pw.cin
+            dwp = ops.conv_wgrad(st.xin, d_raw, 32, pw.cout, ops.conv_taps(1, 1))          # [Cout, 32, 1, 1]
+            dw = dwp[:, :9 * cin, 0, 0].reshape(pw.cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
+        return dx, dw, dgamma, dbeta, dres
     if st.stride == 1:
         if need_dx:
             if dx_add is not None:
@@ -209,7 +244,7 @@ class _ConvBnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, conv, bn, relu, out):
-        y, st = cba_forward(x, conv, bn, relu, residual, out)
+        y, st = cba_forward(x, conv, bn, relu, residual, out, input_needs_grad=ctx.needs_input_grad[0])
         ctx.st = st
         if out is not None:
             ctx.mark_dirty(out)

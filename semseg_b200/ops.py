@@ -171,6 +171,15 @@ def conv_taps_s2(ksize, n):
     return taps
 
 
+def im2col3x3s2(x, cin):
+    """NHWC bf16 x (first `cin` <= 3 channels real) -> patches [N, Ho, Wo, 32] of the 3x3 / stride 2 / pad 1 stem conv."""
+    lib = _lib.load()
+    n, h, w, _, p = _nhwc_meta(x)
+    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 32), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.semseg_im2col3x3s2(_ptr(x), p, n, h, w, int(cin), _ptr(out), _stream()), "semseg_im2col3x3s2")
+    return out
+
+
 def space_to_phases(x):
     """x [N,H,W,C] bf16 -> [4N, (H+1)//2, (W+1)//2, C] (phase-major)."""
     _require_cuda(x)
