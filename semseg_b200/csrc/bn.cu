@@ -306,7 +306,6 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch
                                 const __nv_bfloat16* __restrict__ res, int res_pitch, __nv_bfloat16* __restrict__ y,
                                 int y_pitch, long long M, int C, int relu) {
   const int groups = C >> 3;
-  const long long total = M * groups;
   long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const int c0 = static_cast<int>(idx % groups) << 3;
@@ -500,7 +499,6 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
                                     __nv_bfloat16* __restrict__ dx, int dx_pitch, __nv_bfloat16* __restrict__ dres,
                                     int dres_pitch, float* __restrict__ dgamma_dbeta) {
   const int groups = C >> 3;
-  const long long total = M * groups;
   if (dgamma_dbeta && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       dgamma_dbeta[c] = sums[C + c];

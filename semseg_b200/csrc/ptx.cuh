@@ -113,16 +113,6 @@ __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// 3-D load multicast to every CTA of the cluster named in cta_mask: the box lands at the same CTA-relative smem offset
-// in each destination CTA and completes bytes on the mbarrier at the same CTA-relative offset there.
-__device__ __forceinline__ void tma_load_3d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
-                                                  uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
-      "%4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
-      : "memory");
-}
 // ---- CTA-pair (cta_group::2) forms: both CTAs of a 2-CTA cluster cooperate on one M=256 MMA ---------------------
 // shared::cluster address of `p` (a pointer into my own smem) as seen in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
@@ -221,14 +211,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-// Same, but the arrive is multicast to the mbarrier at the same CTA-relative offset in every CTA of cta_mask.
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
