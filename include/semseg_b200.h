@@ -280,6 +280,15 @@ int semseg_upsample_ce_bwd(const float* logits, int pitch, int N, int h, int w, 
                            int Ho, int Wo, int ignore_index, const float* lse, const float* loss_info,
                            const float* grad_out, float* workspace, float* dlogits, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Step glue: per-class intersection / union / target areas (util/util.py:55-67, called at tool/train.py:286,375).
+ *   counts int32 [3][K] (zeroed by the call): [0] = #(pred == target == k), [1] = #(pred == k) with pred forced to
+ *   ignore_index where target == ignore_index, [2] = #(target == k); union = [1] + [2] - [0].
+ *   write_back != 0 also stores the masked prediction (the reference masks `output` in place).
+ */
+int semseg_iou_hist(void* pred_i64, const void* target_i64, long long n, int K, long long ignore_index, int write_back,
+                    int* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,13 +142,42 @@ def golden_sliding_window():
     print("sliding-window goldens written")
 
 
+def metric_case(seed, shape, K, ignore=255):
+    rng = np.random.default_rng(seed)
+    target = rng.integers(0, K, size=shape).astype(np.int64)
+    pred = np.where(rng.random(shape) < 0.6, target, rng.integers(0, K, size=shape)).astype(np.int64)
+    target[rng.random(shape) < 0.07] = ignore
+    return pred, target
+
+
+METRIC_CASES = [(1, (2, 33, 47), 150), (2, (1, 65, 65), 19), (3, (4000,), 2), (4, (3, 17), 300)]
+
+
+def golden_metrics():
+    """Outputs of the reference's numpy intersectionAndUnion (util/util.py:40-52; the torch twin at :55-67 is the same
+    arithmetic but needs CUDA for histc on int64)."""
+    from util.util import intersectionAndUnion
+    res = {}
+    for seed, shape, K in METRIC_CASES:
+        pred, target = metric_case(seed, shape, K)
+        i, u, t = intersectionAndUnion(pred.copy(), target.copy(), K, 255)
+        key = "s%d" % seed
+        res[key + "/i"], res[key + "/u"], res[key + "/t"] = i.astype(np.int64), u.astype(np.int64), t.astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **res)
+    print("metric goldens written")
+
+
 def main():
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics":
+        golden_metrics()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "sliding":
         golden_sliding_window()
         return
     golden_psamask()
     golden_sliding_window()
+    golden_metrics()
 
     from model.pspnet import PSPNet
     from model.psanet import PSANet

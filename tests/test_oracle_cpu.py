@@ -113,3 +113,15 @@ def test_torch_oracle_pspnet50_matches_reference_goldens(golden_dir):
 def test_torch_oracle_psanet50_matches_reference_goldens(golden_dir):
     _check_model("psanet50_65", "psa", golden_dir, lambda: util.build_psanet(50, 150, mask=9),
                  dict(mask_h=9, mask_w=9))
+
+
+def test_metric_oracle_matches_reference_goldens(golden_dir):
+    """oracle/metrics.py vs the reference's own numpy intersectionAndUnion (util/util.py:40-52), incl. K > ignore_index
+    where label 255 is a countable class."""
+    from oracle import metrics as om
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    for seed, shape, K in util.METRIC_CASES:
+        pred, target = util.metric_case(seed, shape, K)
+        i, u, t, _ = om.intersection_and_union(pred, target, K, 255)
+        key = "s%d" % seed
+        assert np.array_equal(i, g[key + "/i"]) and np.array_equal(u, g[key + "/u"]) and np.array_equal(t, g[key + "/t"])

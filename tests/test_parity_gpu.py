@@ -610,3 +610,25 @@ def test_sliding_window_engine_bit_identical_to_serial_oracle():
     assert np.allclose(fast_scores, ref_scores, rtol=0, atol=5e-6) and (fast_amax != ref_amax).mean() < 1e-3
     one = inference.net_process(model, image[:crop, :crop].copy(), c["mean"], c["std"])
     assert np.array_equal(one, osw.score_crop(model, image[:crop, :crop].copy(), c["mean"], c["std"]))
+
+
+# ------------------------------------------------------------------------------------------------ step-glue metrics
+def test_intersection_and_union_kernel_exact():
+    """one-pass integer histogram vs the oracle (pinned to the reference's numpy function) — exact counts,
+    same in-place masking of the prediction, float32 [K] device tensors like torch.histc returns."""
+    from oracle import metrics as om
+    from semseg_b200.metrics import intersectionAndUnionGPU
+    cases = util.METRIC_CASES + [(9, (16, 473, 473), 150)]
+    for seed, shape, K in cases:
+        pred, target = util.metric_case(seed, shape, K)
+        o = torch.from_numpy(pred).cuda()
+        t = torch.from_numpy(target).cuda()
+        i, u, a = intersectionAndUnionGPU(o, t, K, 255)
+        ri, ru, rt, masked = om.intersection_and_union(pred, target, K, 255)
+        assert i.dtype == torch.float32 and tuple(i.shape) == (K,) and i.is_cuda
+        assert np.array_equal(i.cpu().numpy().astype(np.int64), ri)
+        assert np.array_equal(u.cpu().numpy().astype(np.int64), ru)
+        assert np.array_equal(a.cpu().numpy().astype(np.int64), rt)
+        assert np.array_equal(o.cpu().numpy().reshape(-1), masked)          # the reference masks `output` in place
+    with pytest.raises(Exception):
+        intersectionAndUnionGPU(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 3)

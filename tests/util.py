@@ -65,3 +65,15 @@ SW_CFG = dict(classes=5, base_size=64, crop_h=33, crop_w=33, scales=[0.75, 1.0, 
 def sw_image(seed=9, h=40, w=60):
     rng = np.random.default_rng(seed)
     return (rng.random((h, w, 3)) * 255).astype(np.float32)
+
+
+def metric_case(seed, shape, K, ignore=255):
+    """Synthetic (prediction, target) pair of the metric goldens (identical to tests/golden/_ref_worker.py)."""
+    rng = np.random.default_rng(seed)
+    target = rng.integers(0, K, size=shape).astype(np.int64)
+    pred = np.where(rng.random(shape) < 0.6, target, rng.integers(0, K, size=shape)).astype(np.int64)
+    target[rng.random(shape) < 0.07] = ignore
+    return pred, target
+
+
+METRIC_CASES = [(1, (2, 33, 47), 150), (2, (1, 65, 65), 19), (3, (4000,), 2), (4, (3, 17), 300)]
