@@ -44,21 +44,30 @@ def test_ctypes_binding_covers_header():
 
 
 def test_struct_layout_matches_header():
-    """sizeof(semseg_conv_desc / semseg_wgrad_desc) as the C compiler sees them == the ctypes mirrors."""
+    """sizeof / offsets of the ABI structs as the C compiler sees them == the ctypes mirrors."""
     import tempfile
     prog = r'''
 #include <stdio.h>
 #include "semseg_b200.h"
-int main(void) { printf("%zu %zu\n", sizeof(semseg_conv_desc), sizeof(semseg_wgrad_desc)); return 0; }
+#include <stddef.h>
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(semseg_conv_desc), sizeof(semseg_wgrad_desc), sizeof(semseg_pack_item),
+         offsetof(semseg_pack_item, Cout), offsetof(semseg_pack_item, tile0), offsetof(semseg_pack_item, tiles_ci));
+  return 0;
+}
 '''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
         open(c, "w").write(prog)
         exe = os.path.join(d, "t")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
-        a, b = map(int, subprocess.check_output([exe]).split())
+        a, b, c, o_cout, o_tile0, o_tiles = map(int, subprocess.check_output([exe]).split())
     assert a == ctypes.sizeof(_lib.ConvDesc)
     assert b == ctypes.sizeof(_lib.WgradDesc)
+    # the item table of semseg_pack_weights_multi is built by ctypes and read by the device code
+    assert c == ctypes.sizeof(_lib.PackItem)
+    assert (o_cout, o_tile0, o_tiles) == (_lib.PackItem.Cout.offset, _lib.PackItem.tile0.offset,
+                                          _lib.PackItem.tiles_ci.offset)
 
 
 def test_invalid_arguments_return_error_codes_without_gpu():
@@ -71,3 +80,8 @@ def test_invalid_arguments_return_error_codes_without_gpu():
     d = _lib.ConvDesc()
     assert lib.semseg_conv_fprop(ctypes.byref(d), None) == -1
     assert lib.semseg_conv_stats_rows(1, 8, 16, 64) == 4
+    assert lib.semseg_iou_hist(ctypes.c_void_p(16), ctypes.c_void_p(16), 10, 0, 255, 1, ctypes.c_void_p(16), None) == -1
+    assert b"iou_hist" in lib.semseg_last_error()
+    assert lib.semseg_im2col3x3s2(ctypes.c_void_p(16), 8, 1, 9, 9, 4, ctypes.c_void_p(16), None) == -1
+    assert b"im2col3x3s2" in lib.semseg_last_error()
+    assert lib.semseg_pack_weights_multi(None, 1, 1, 9, None) == -1
