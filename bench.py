@@ -300,9 +300,9 @@ def run_b200_arm(args):
                     args.batch, fmap, fmap), "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
-                # `ncu --set full` capture (profiles/r1_ncu_summary.md): 733.97 MB + 60.97 MB per launch; the
-                # algorithmic bytes are 510 MB in + 59 MB out.
-                "traffic": 794.9e6 if (args.batch, fmap) == (16, 60) else None, "traffic_unit": "bytes/launch",
+                # `ncu --set full` capture of the final build (profiles/r1_ncu_full_final_key_metrics.csv, first row):
+                # 738.1 MB + 72.5 MB per launch; the algorithmic bytes are 510 MB in + 59 MB out.
+                "traffic": 810.6e6 if (args.batch, fmap) == (16, 60) else None, "traffic_unit": "bytes/launch",
                 "ms_per_launch": t_k, "peak_source": pk["source"] +
                 " burst bf16 (kernel timed alone)"}
         del xa, w, pw, flush
