@@ -2,8 +2,8 @@
 """Benchmark of the semseg training hot path (BASELINE.json metric: PSPNet50 473x473 training images/sec).
 
     python bench.py --gpus N --steps K --warmup W            # B200-native arm (this repository)
-    python bench.py --impl reference --gpus N ...            # reference arm: the CPU restatement of the
-                                                             # reference's PyTorch path (oracle/) on host cores
+    python bench.py --impl reference --gpus N ...            # reference arm: the reference's OWN modules
+                                                             # (baseline/_ref/model/pspnet.py) on the host cores
 
 A "step" is the body of the reference's training loop, tool/train.py:267-276: H2D of a pinned synthetic batch,
 model(input, target) (forward incl. both cross-entropy losses and the argmax), loss = main + 0.4*aux, zero_grad,
@@ -22,9 +22,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "PSPNet50 473x473 training images/sec"
-CONV_GFLOP_PER_IMG_TRAIN = 1022.8      # fwd+bwd conv FLOPs per image, PSPNet50@473/150 cls
-CLS_CONV_GFLOP_PER_IMG = 135.9         # cls 3x3 4096->512 on 60x60, forward
+# fwd+bwd conv FLOPs (2*MAC) per image of the measured configurations
+CONV_GFLOP_PER_IMG_TRAIN = {("psp", 50, 473, 150): 1022.8, ("psp", 101, 473, 150): 1431.9,
+                            ("psp", 101, 713, 19): 3217.6, ("psa", 50, 465, 150): 1071.0}
 
 
 def parse():
@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=2, help="images per step of the CPU arms (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stock-gpu", action="store_true")
+    ap.add_argument("--no-parity-mode", action="store_true")
     return ap.parse_args()
 
 
@@ -118,16 +119,56 @@ def build_optimizer(model, arch):
     return torch.optim.SGD(groups, lr=0.01, momentum=0.9, weight_decay=1e-4)
 
 
-# ---------------------------------------------------------------------------------------------------- CPU arms
+# ---------------------------------------------------------------------------------------------------- reference arms
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_available():
+    """The unmodified reference tree under baseline/_ref (baseline/install_reference.py; git-ignored, travels with the
+    snapshot). In the build container it is (re)created from /root/reference on demand."""
+    if not os.path.isdir(os.path.join(REF_DIR, "model")):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import install_reference
+            install_reference.install()
+        except Exception:      # noqa: BLE001
+            pass
+        finally:
+            sys.path.pop(0)
+    return os.path.isdir(os.path.join(REF_DIR, "model"))
+
+
+def run_reference_modules(args, device, batch, steps, warmup, threads=0, timeout=1500):
+    """The reference's own model/pspnet.py / model/psanet.py stepping on `device` in a subprocess whose cwd and
+    PYTHONPATH are baseline/_ref only (its `model` package must not meet this repository's). -> dict from the runner."""
+    import subprocess
+    env = dict(os.environ)
+    env["PYTHONPATH"] = REF_DIR
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_reference.py"), "--device", device, "--arch", args.arch,
+           "--layers", str(args.layers), "--classes", str(args.classes), "--size", str(args.size), "--batch",
+           str(batch), "--steps", str(steps), "--warmup", str(warmup), "--threads", str(threads)]
+    r = subprocess.run(cmd, cwd=REF_DIR, env=env, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError("reference runner failed: %s" % r.stderr.strip().splitlines()[-1:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
 def cpu_reference_run(args, steps, warmup):
-    """The reference's CPU PyTorch path (oracle restatement: same ATen ops, fp32) on all host cores."""
+    """The reference's CPU PyTorch path on the host cores: its own modules from baseline/_ref (kind "reference"); the
+    fp32 oracle restatement (kind "port") only where the reference tree is absent."""
+    # oneDNN scales poorly past ~32 threads on a 2-image batch (128 threads were 10x slower than 32 on the GPU box),
+    # so the CPU arms use min(host cores, 32) threads and report that number as `cores`.
+    cores = min(os.cpu_count() or 1, 32)
+    if reference_available():
+        d = run_reference_modules(args, "cpu", args.cpu_batch, steps, warmup, threads=cores)
+        return dict(value=d["images_per_sec"], seconds=d["seconds"], cores=d["threads"], kind="reference",
+                    what="reference modules %s (baseline/_ref), fp32, torch %s" % (d["module_file"], d["torch"]))
     import torch
     from oracle.torch_oracle import Oracle
     from semseg_b200.pspnet import PSPNet
     from semseg_b200.psanet import PSANet
-    # oneDNN scales poorly past ~32 threads on a 2-image batch (128 threads were 10x slower than 32 on the GPU box),
-    # so the CPU arms use min(host cores, 32) threads and report that number as `cores`.
-    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     if args.arch == "psp":
@@ -157,7 +198,19 @@ def cpu_reference_run(args, steps, warmup):
         opt.step()
         times.append(time.perf_counter() - t0)
     t = sum(times[warmup:])
-    return dict(value=args.cpu_batch * steps / t, seconds=t, cores=cores)
+    return dict(value=args.cpu_batch * steps / t, seconds=t, cores=cores, kind="port",
+                what="oracle/torch_oracle.py restatement (baseline/_ref absent)")
+
+
+def workload_name(args):
+    return "%s%d %s-shape %dx%d, %d classes, synthetic training step (tool/train.py:267-276), %d images/GPU" % (
+        "PSPNet" if args.arch == "psp" else "PSANet", args.layers, "ADE20K" if args.classes == 150 else "Cityscapes"
+        if args.classes == 19 else "custom", args.size, args.size, args.classes, args.batch)
+
+
+def metric_name(args):
+    return "%s%d %dx%d training images/sec" % ("PSPNet" if args.arch == "psp" else "PSANet", args.layers, args.size,
+                                                 args.size)
 
 
 def run_reference_arm(args):
@@ -166,18 +219,15 @@ def run_reference_arm(args):
         return
     steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
     r = cpu_reference_run(args, steps, warmup)
-    sample = "%d timed steps (of --steps %d) x %d images, %s%d %dx%d, fp32, min(host cores, 32) threads" % (
-        steps, args.steps, args.cpu_batch, "PSPNet" if args.arch == "psp" else "PSANet", args.layers, args.size,
-        args.size)
+    sample = "%d timed steps (of --steps %d) x %d images of the workload, fp32, min(host cores, 32) threads; %s" % (
+        steps, args.steps, args.cpu_batch, r["what"])
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/sec", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s%d ADE20K-shape %dx%d, %d classes, synthetic training step (tool/train.py:267-276), "
-                               "%d images/GPU" % ("PSPNet" if args.arch == "psp" else "PSANet", args.layers,
-                                                  args.size, args.size, args.classes, args.batch),
-                   "sample": "CPU arm times %d images/step of that workload" % args.cpu_batch},
-        "cpu_baseline": {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": "port",
+        "impl": "reference", "metric": metric_name(args), "value": r["value"], "unit": "images/sec",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args),
+                   "sample": "CPU arm times %d images/step of that workload (bounded sample)" % args.cpu_batch},
+        "cpu_baseline": {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": r["kind"],
                          "sample": sample},
         "e2e": {"value": r["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -271,6 +321,24 @@ def run_b200_arm(args):
     value = n_img / (ms_dev / 1e3)
     e2e_value = n_img / (ms_e2e / 1e3)
 
+    # ---- the same step in the parity-precision operand mode (bf16x3: hi/lo bf16 pairs, three MMA segments per K block;
+    #      the mode whose eval logits match the fp32 reference to 1e-3 with identical argmax, tests/test_parity_x3_gpu.py)
+    parity = None
+    if not args.no_parity_mode:
+        from semseg_b200 import precision
+        psteps = max(1, min(args.steps, 5))
+        try:
+            with precision.mode("bf16x3"):
+                for _ in range(2):
+                    step(x_dev, y_dev)
+                ms_p = timed(lambda: step(x_dev, y_dev), psteps)
+            parity = {"dtype": "bf16x3", "value": args.batch * world * psteps / (ms_p / 1e3), "unit": "images/sec",
+                      "ms_per_step": ms_p / psteps, "steps": psteps,
+                      "what": "same training step with (hi, lo) bf16 activations / weights and x_hi*w_hi + x_lo*w_hi + "
+                              "x_hi*w_lo accumulation in fp32 (16-bit mantissa operands >= the reference's TF32 cuDNN path)"}
+        except Exception as e:      # noqa: BLE001
+            parity = {"dtype": "bf16x3", "error": str(e)[:300]}
+
     # ---- roofline of the dominant kernel: the cls-head 3x3 conv 4096->512 fprop, timed alone with CUDA events
     pk = peaks()
     roof = None
@@ -314,14 +382,16 @@ def run_b200_arm(args):
             dist.destroy_process_group()
         return
 
-    step_tflops = CONV_GFLOP_PER_IMG_TRAIN * args.batch * world * args.steps / (ms_dev / 1e3) / 1e3
+    gflop_img = CONV_GFLOP_PER_IMG_TRAIN.get((args.arch, args.layers, args.size, args.classes))
+    step_tflops = gflop_img * args.batch * world * args.steps / (ms_dev / 1e3) / 1e3 if gflop_img else None
     line = {
-        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(args), "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "%s%d ADE20K-shape %dx%d, %d classes, synthetic training step (tool/train.py:267-276), "
-                               "%d images/GPU" % ("PSPNet" if args.arch == "psp" else "PSANet", args.layers,
-                                                  args.size, args.size, args.classes, args.batch),
+        "dtype_note": "value / e2e: single-pass bf16 operands (speed configuration); parity_mode: bf16x3 (the "
+                      "reference-precision configuration)",
+        "parity_mode": parity,
+        "config": {"workload": workload_name(args),
                    "global_batch": args.batch * world, "parallelism": "dp%d" % world,
                    "l2": "inputs larger than L2: each step streams > 10 GB of activations through the 126 MB L2",
                    "optimizer": "SGD momentum 0.9 wd 1e-4, 8 param groups", "sync_bn": world > 1,
@@ -332,7 +402,7 @@ def run_b200_arm(args):
         "clocks": sampler.result(),
         "roofline": roof,
         "step_conv_tflops": step_tflops,
-        "step_conv_frac_of_sustained_peak": step_tflops / (pk["bf16_tflops_sustained"] * world),
+        "step_conv_frac_of_sustained_peak": step_tflops / (pk["bf16_tflops_sustained"] * world) if step_tflops else None,
     }
     if world == 1 and not args.no_stock_gpu:
         try:
@@ -341,55 +411,28 @@ def run_b200_arm(args):
             line["stock_gpu_baseline"] = {"error": str(e)[:200]}
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, 2, 1)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": "port",
-                                "sample": "2 timed steps x %d images of the same workload (fp32 oracle restatement of "
-                                          "the reference's PyTorch path, min(host cores, 32) threads)" % args.cpu_batch}
+        line["cpu_baseline"] = {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": r["kind"],
+                                "sample": "2 timed steps x %d images of the same workload, fp32, min(host cores, 32) "
+                                          "threads; %s" % (args.cpu_batch, r["what"])}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def stock_gpu_baseline(args, dev):
-    """The reference's stock GPU path restated (fp32 NCHW, cuDNN, torch default flags incl. TF32 convs) on the same
-    GPU and workload — the optimisation target's denominator. Informational extra field."""
+    """The optimisation target's denominator: the reference's own modules on the same GPU and workload
+    — fp32 NCHW, cuDNN, torch default flags (TF32 convolutions), nn.DataParallel as tool/train.py:159 — through
+    baseline/run_reference.py. Informational extra field (the driver's ratio uses the CPU reference arm)."""
     import torch
-    from oracle.torch_oracle import Oracle
-    from semseg_b200.pspnet import PSPNet
-    torch.backends.cudnn.allow_tf32 = True
-    torch.manual_seed(0)
-    m = PSPNet(layers=args.layers, classes=args.classes, zoom_factor=8, pretrained=False)
-    params = {k for k, _ in m.named_parameters()}
-    sd = {k: v.detach().clone().to(dev) for k, v in m.state_dict().items()}
-    plist = []
-    for k, v in sd.items():
-        if k in params:
-            v.requires_grad_(True)
-            plist.append(v)
-    orc = Oracle(sd, arch="psp", layers=args.layers, classes=args.classes, dropout=0.1).train()
-    opt = torch.optim.SGD(plist, lr=0.01, momentum=0.9, weight_decay=1e-4)
-    x, y = synth_batch(args.batch, args.size, args.classes, 0)
-    x, y = x.to(dev), y.to(dev)
-
-    def step():
-        _, ml, al = orc.forward(x, y)
-        loss = ml + 0.4 * al
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    n = 5
-    for _ in range(n):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    return {"value": args.batch / (ms / 1e3), "unit": "images/sec", "ms_per_step": ms,
-            "what": "same network in stock PyTorch: fp32 NCHW, cuDNN (TF32 convs allowed = torch default), bs%d"
-                    % args.batch}
+    torch.cuda.empty_cache()
+    if not reference_available():
+        return {"error": "baseline/_ref absent"}
+    d = run_reference_modules(args, "cuda", args.batch, 5, 3)
+    ms = 1e3 * d["seconds"] / d["steps"]
+    return {"value": d["images_per_sec"], "unit": "images/sec", "ms_per_step": ms, "kind": "reference",
+            "what": "reference modules %s under nn.DataParallel on the same GPU: fp32 NCHW, cuDNN, torch default flags "
+                    "(TF32 convs %s), bs%d, H2D of the pinned batch inside the step" % (d["module_file"],
+                                                                                      d["tf32_conv"], args.batch)}
 
 
 def main():

@@ -98,8 +98,33 @@ typedef struct semseg_conv_desc {
   /* RAW mode statistics: stats_partial [rows][3][Cout] = per epilogue-warp (sum, sum of squares, count) of the stored
    * bf16 outputs per channel, rows = semseg_conv_stats_rows(); NULL to skip. The kernel zeroes and fills every row. */
   float* stats_partial;
+  /* bf16x3 operand mode (split storage): lo planes of x / y / residual (same shapes and pitches as the hi planes);
+   * all NULL for plain bf16. With x_lo set, w must hold the lo slab directly behind the hi slab (w_split != 0,
+   * semseg_pack_weights(..., split = 1)) and every K block is accumulated as x_hi*w_hi + x_lo*w_hi + x_hi*w_lo;
+   * statistics are those of hi + lo. */
+  const void* x_lo;
+  void* y_lo;
+  const void* residual_lo;
+  int32_t w_split;
+  /* K slicing (F32 epilogue only; 0 or 1 = off): the K blocks (64-channel block x tap) are cut into k_slices ranges,
+   * slice s writes its fp32 partial to out_f32 + s*slice_stride (elements); the bias is added by slice 0 only. Used by
+   * the bf16x3 mode to bound the length of one tensor-core accumulation chain (semseg_conv_k_slices,
+   * semseg_conv_splitk_finish). */
+  int32_t k_slices;
+  int64_t slice_stride;
 } semseg_conv_desc;
 
+/* Number of K slices such that one slice holds at most max_kblocks K blocks (64-channel block x tap). */
+int semseg_conv_k_slices(int Cin, int taps, int max_kblocks);
+/* Sum the k_slices fp32 partials [k_slices][M][part_pitch] of a K-sliced conv in fp32 (round-to-nearest) and finish
+ * like the conv epilogue would have: RAW (y = sum; optional statistics rows [rows][3][C] = (sum, sum of squares, count)
+ * per pixel chunk, rows = semseg_conv_splitk_rows(M)) or AFFINE (y = act(sum*scale + shift + residual)). y (and the
+ * residual) may be split (hi, lo) or plain. C % 64 == 0. */
+int semseg_conv_splitk_rows(int M);
+int semseg_conv_splitk_finish(const float* partial, int k_slices, long long slice_stride, int part_pitch, int M, int C,
+                              int epi_mode, int relu, const float* scale, const float* shift, const void* residual,
+                              const void* residual_lo, int res_pitch, void* y, void* y_lo, int y_pitch,
+                              float* stats_partial, void* stream);
 /* Rows of the statistics buffer (= 4 x CTAs launched) for an [N,H,W] x Cout output. */
 int semseg_conv_stats_rows(int N, int H, int W, int Cout);
 int semseg_conv_fprop(const semseg_conv_desc* d, void* stream);
@@ -119,6 +144,9 @@ typedef struct semseg_wgrad_desc {
   int32_t img_mul, img_add[SEMSEG_MAX_TAPS];
   float* dw_partial;
   int32_t n_splits; /* in: 0 = let the library choose; out (via semseg_conv_wgrad_splits) */
+  /* bf16x3 operand mode: lo planes of x and dy (both or neither); dy_hi*x_hi + dy_lo*x_hi + dy_hi*x_lo. */
+  const void* x_lo;
+  const void* dy_lo;
 } semseg_wgrad_desc;
 
 int semseg_conv_wgrad_splits(const semseg_wgrad_desc* d);
@@ -132,7 +160,7 @@ int semseg_wgrad_reduce(const float* dw_partial, int n_splits, int taps, int Cou
  *   wd bf16 [taps][rows_d][cols_d]  (wd[t][ci][co], zero padded)   — dgrad B operand
  * Either output may be NULL. */
 int semseg_pack_weights(const float* w_oihw, int Cout, int Cin, int taps, void* wf, int rows_f, int cols_f,
-                        void* wd, int rows_d, int cols_d, void* stream);
+                        void* wd, int rows_d, int cols_d, int split, void* stream);
 
 /* The same packing for every conv of a model in one launch (torch re-packs after each optimizer step; 2 x 63 small
  * launches per step for PSPNet50 otherwise). `items` is an array in DEVICE memory, sorted by tile0; an item's tiles are
@@ -145,17 +173,17 @@ typedef struct semseg_pack_item {
   int Cout, Cin, taps;
   int cols_f, cols_d;
   int tile0, tiles_ci;
-  int reserved;
+  int split; /* != 0: lo slabs follow the hi slabs (wf + taps*Cout*cols_f, wd + taps*Cin*cols_d) */
 } semseg_pack_item;
 int semseg_pack_weights_multi(const semseg_pack_item* items_dev, int n_items, int n_tiles, int max_taps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout conversion at the module boundary.
  */
-int semseg_nchw_f32_to_nhwc_bf16(const float* in, void* out, int N, int C, int H, int W, int out_pitch,
+int semseg_nchw_f32_to_nhwc_bf16(const float* in, void* out, void* out_lo, int N, int C, int H, int W, int out_pitch,
                                  void* stream);
-int semseg_nhwc_bf16_to_nchw_f32(const void* in, float* out, int N, int C, int H, int W, int in_pitch,
-                                 void* stream);
+int semseg_nhwc_bf16_to_nchw_f32(const void* in, const void* in_lo, float* out, int N, int C, int H, int W,
+                                 int in_pitch, void* stream);
 int semseg_nhwc_f32_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W, int in_pitch,
                                 void* stream);
 
@@ -201,45 +229,57 @@ int semseg_bn_finalize_p2p(const float* stats_partial, int rows, int C, const fl
                            float eps, float momentum, float* running_mean, float* running_var, float* mean_invstd,
                            float* scale_shift, void* const* peer_bufs, void* const* peer_flags, void* counter,
                            int world, int rank, int slot, int slot_floats, unsigned seq, void* stream);
-int semseg_bn_bwd_reduce_p2p(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x, int x_pitch,
-                             const float* mean_invstd, const float* scale_shift, int M, int C, int relu,
-                             float* workspace, long long workspace_floats, float* sums_local, float* sums_total,
+int semseg_bn_bwd_reduce_p2p(const void* dy, const void* dy_lo, int dy_pitch, const void* y, const void* y_lo,
+                             int y_pitch, const void* x, const void* x_lo, int x_pitch, const float* mean_invstd,
+                             const float* scale_shift, int M, int C, int relu, float* workspace,
+                             long long workspace_floats, float* sums_local, float* sums_total,
                              void* const* peer_bufs, void* const* peer_flags, void* counter, int world, int rank,
                              int slot, int slot_floats, unsigned seq, void* stream);
 /* Eval-mode folding: scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
 int semseg_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, int C, float* scale_shift, void* stream);
 /* y = act(x*scale[c] + shift[c] + residual). */
-int semseg_bn_apply(const void* x, int x_pitch, const float* scale_shift, const void* residual, int res_pitch,
-                    void* y, int y_pitch, int M, int C, int relu, void* stream);
+int semseg_bn_apply(const void* x, const void* x_lo, int x_pitch, const float* scale_shift, const void* residual,
+                    const void* residual_lo, int res_pitch, void* y, void* y_lo, int y_pitch, int M, int C, int relu,
+                    void* stream);
 /* Backward reduce: with dz = dy * (y > 0 if relu) and xhat = (x - mean)*invstd,
  *   sums [2][C] = (sum dz, sum dz*xhat). y may be NULL when relu == 0; when relu != 0 and y == NULL the mask is
  *   recomputed as fma(x, scale, shift) > 0 from scale_shift [2][C] (valid when the forward had no residual). */
-int semseg_bn_bwd_reduce(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x, int x_pitch,
-                         const float* mean_invstd, const float* scale_shift, int M, int C, int relu, float* workspace,
+int semseg_bn_bwd_reduce(const void* dy, const void* dy_lo, int dy_pitch, const void* y, const void* y_lo, int y_pitch,
+                         const void* x, const void* x_lo, int x_pitch, const float* mean_invstd,
+                         const float* scale_shift, int M, int C, int relu, float* workspace,
                          long long workspace_floats, float* sums, void* stream);
-/* Backward apply: dx = gamma*invstd*(dz - sum_dz/count - xhat*sum_dzxhat/count) (bf16);
- *   dres (optional) = dz (bf16); dgamma = sum_dzxhat, dbeta = sum_dz written to dgamma_dbeta [2][C].
+/* Backward apply: dx = gamma*invstd*(dz - sum_dz/count - xhat*sum_dzxhat/count);
+ *   dres (optional) = dz; dgamma = sum_dzxhat, dbeta = sum_dz written to dgamma_dbeta [2][C].
  *   count = total number of samples per channel across all ranks. */
-int semseg_bn_bwd_apply(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x, int x_pitch,
-                        const float* mean_invstd, const float* gamma, const float* scale_shift, const float* sums,
-                        float count, int M,
-                        int C, int relu, void* dx, int dx_pitch, void* dres, int dres_pitch,
-                        float* dgamma_dbeta, void* stream);
-/* dz = dy * (y > 0); plain ReLU backward for tensors without BN in between. */
-int semseg_relu_bwd(const void* dy, int dy_pitch, const void* y, int y_pitch, void* dz, int dz_pitch, int M,
-                    int C, void* stream);
-/* out = a + b (bf16 NHWC, used to merge gradient branches). */
-int semseg_add_bf16(const void* a, int a_pitch, const void* b, int b_pitch, void* out, int out_pitch, int M,
-                    int C, void* stream);
+int semseg_bn_bwd_apply(const void* dy, const void* dy_lo, int dy_pitch, const void* y, const void* y_lo, int y_pitch,
+                        const void* x, const void* x_lo, int x_pitch, const float* mean_invstd, const float* gamma,
+                        const float* scale_shift, const float* sums, float count, int M, int C, int relu, void* dx,
+                        void* dx_lo, int dx_pitch, void* dres, void* dres_lo, int dres_pitch, float* dgamma_dbeta,
+                        void* stream);
+/* out = a + b (merges gradient branches; split-aware, unlike an elementwise add of the two planes). */
+int semseg_add_act(const void* a, const void* a_lo, int a_pitch, const void* b, const void* b_lo, int b_pitch,
+                   void* out, void* out_lo, int out_pitch, int M, int C, void* stream);
+/* out[n, p, c] = x[n, p, c] * scale[n*C + c] for p < HW: nn.Dropout2d's per-(image, channel) factor
+ * (model/pspnet.py:68,76) and its backward. */
+int semseg_scale_nc(const void* x, const void* x_lo, int x_pitch, const float* scale, void* out, void* out_lo,
+                    int out_pitch, int N, int HW, int C, void* stream);
+/* fp32 rows [M][in_pitch] (C columns used) -> activation rows [M][out_pitch], columns C..Cp-1 zero (Cp % 8 == 0). */
+int semseg_f32_to_act(const float* in, int in_pitch, void* out, void* out_lo, int out_pitch, long long M, int C,
+                      int Cp, void* stream);
+/* activation rows [M][in_pitch] (C % 8 == 0 columns) -> fp32 rows [M][out_pitch]. */
+int semseg_act_to_f32(const void* in, const void* in_lo, int in_pitch, float* out, int out_pitch, long long M, int C,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC bf16 (model/resnet.py:115): y [N,Ho,Wo,C] with
  * Ho = (H-1)/2+1; argcode uint8 [N,Ho,Wo,C] (or NULL) = window position 0..8 of the arg-max (first maximum in window
  * order, as ATen). Backward gathers with those codes: dx [N,H,W,C] dense, deterministic, no atomics.
  */
-int semseg_maxpool3x3s2_fwd(const void* x, void* y, void* argcode, int N, int H, int W, int C, void* stream);
-int semseg_maxpool3x3s2_bwd(const void* argcode, const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+int semseg_maxpool3x3s2_fwd(const void* x, const void* x_lo, void* y, void* y_lo, void* argcode, int N, int H, int W,
+                            int C, void* stream);
+int semseg_maxpool3x3s2_bwd(const void* argcode, const void* dy, const void* dy_lo, void* dx, void* dx_lo, int N,
+                            int H, int W, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pyramid pooling module data movement (model/pspnet.py:12-26), NHWC bf16, all bins in one launch.
@@ -252,14 +292,16 @@ int semseg_maxpool3x3s2_bwd(const void* argcode, const void* dy, void* dx, int N
  *                         feats_k to H x W (the torch.cat of model/pspnet.py:26 written in place).
  *   ppm_upsample_bwd    : dfeats_k = adjoint of the bilinear upsample applied to dout[..., c_off + k*Cr : ...].
  */
-int semseg_ppm_pool(const void* x, int x_pitch, int N, int H, int W, int C, const int* bins, void* const* pooled,
-                    int nb, void* stream);
-int semseg_ppm_pool_bwd(void* const* dpooled, const int* bins, int nb, int N, int H, int W, int C, void* dx,
-                        int dx_pitch, const void* add, int add_pitch, void* stream);
-int semseg_ppm_upsample_concat(const void* x, int x_pitch, void* const* feats, const int* bins, int nb, int N, int H,
-                               int W, int C, int Cr, void* out, int out_pitch, void* stream);
-int semseg_ppm_upsample_bwd(const void* dout, int dout_pitch, int c_off, void* const* dfeats, const int* bins, int nb,
-                            int N, int H, int W, int Cr, void* stream);
+int semseg_ppm_pool(const void* x, const void* x_lo, int x_pitch, int N, int H, int W, int C, const int* bins,
+                    void* const* pooled, void* const* pooled_lo, int nb, void* stream);
+int semseg_ppm_pool_bwd(void* const* dpooled, void* const* dpooled_lo, const int* bins, int nb, int N, int H, int W,
+                        int C, void* dx, void* dx_lo, int dx_pitch, const void* add, const void* add_lo, int add_pitch,
+                        void* stream);
+int semseg_ppm_upsample_concat(const void* x, const void* x_lo, int x_pitch, void* const* feats, void* const* feats_lo,
+                               const int* bins, int nb, int N, int H, int W, int C, int Cr, void* out, void* out_lo,
+                               int out_pitch, void* stream);
+int semseg_ppm_upsample_bwd(const void* dout, const void* dout_lo, int dout_pitch, int c_off, void* const* dfeats,
+                            void* const* dfeats_lo, const int* bins, int nb, int N, int H, int W, int Cr, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused logit upsample (bilinear, align_corners=True, x8) + cross-entropy (ignore_index, mean over valid

@@ -27,7 +27,7 @@ class PackItem(ctypes.Structure):
         ("Cout", c_i32), ("Cin", c_i32), ("taps", c_i32),
         ("cols_f", c_i32), ("cols_d", c_i32),
         ("tile0", c_i32), ("tiles_ci", c_i32),
-        ("reserved", c_i32),
+        ("split", c_i32),
     ]
 
 
@@ -49,6 +49,9 @@ class ConvDesc(ctypes.Structure):
         ("residual", c_vp), ("res_pitch", c_i32),
         ("out_f32", c_vp), ("out_pitch", c_i32),
         ("stats_partial", c_vp),
+        ("x_lo", c_vp), ("y_lo", c_vp), ("residual_lo", c_vp),
+        ("w_split", c_i32),
+        ("k_slices", c_i32), ("slice_stride", ctypes.c_int64),
     ]
 
 
@@ -65,6 +68,7 @@ class WgradDesc(ctypes.Structure):
         ("img_mul", c_i32), ("img_add", I9),
         ("dw_partial", c_vp),
         ("n_splits", c_i32),
+        ("x_lo", c_vp), ("dy_lo", c_vp),
     ]
 
 
@@ -77,16 +81,20 @@ SIGNATURES = {
     "semseg_psamask_fwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_psamask_bwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_conv_stats_rows": (c_int, [c_int, c_int, c_int, c_int]),
+    "semseg_conv_k_slices": (c_int, [c_int, c_int, c_int]),
+    "semseg_conv_splitk_rows": (c_int, [c_int]),
+    "semseg_conv_splitk_finish": (c_int, [c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                                          c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
     "semseg_conv_fprop": (c_int, [ctypes.POINTER(ConvDesc), c_vp]),
     "semseg_conv_wgrad_splits": (c_int, [ctypes.POINTER(WgradDesc)]),
     "semseg_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_vp]),
     "semseg_wgrad_reduce": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
-    "semseg_pack_weights": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp]),
+    "semseg_pack_weights": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp]),
     "semseg_pack_weights_multi": (c_int, [c_vp, c_int, c_int, c_int, c_vp]),
     "semseg_iou_hist": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_int, ctypes.c_longlong, c_int, c_vp, c_vp]),
     "semseg_im2col3x3s2": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
-    "semseg_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
-    "semseg_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_nhwc_f32_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_space_to_phases": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "semseg_phases_to_space": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
@@ -97,24 +105,29 @@ SIGNATURES = {
     "semseg_bn_finalize_partials": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "semseg_bn_finalize_p2p": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                        c_vp, c_int, c_int, c_int, c_int, ctypes.c_uint, c_vp]),
-    "semseg_bn_bwd_reduce_p2p": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp,
-                                         c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
-                                         ctypes.c_uint, c_vp]),
+    "semseg_bn_bwd_reduce_p2p": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int,
+                                         c_int, c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int,
+                                         c_int, ctypes.c_uint, c_vp]),
     "semseg_bn_fold_eval": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_vp, c_vp]),
-    "semseg_bn_apply": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
-    "semseg_bn_bwd_reduce": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp,
-                                     c_ll, c_vp, c_vp]),
-    "semseg_bn_bwd_apply": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_int,
-                                    c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
-    "semseg_relu_bwd": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp]),
-    "semseg_add_bf16": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp]),
-    "semseg_maxpool3x3s2_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
-    "semseg_maxpool3x3s2_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
-    "semseg_ppm_pool": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
-    "semseg_ppm_pool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
-    "semseg_ppm_upsample_concat": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
-                                           c_int, c_vp]),
-    "semseg_ppm_upsample_bwd": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_bn_apply": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int,
+                                c_vp]),
+    "semseg_bn_bwd_reduce": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int,
+                                     c_int, c_vp, c_ll, c_vp, c_vp]),
+    "semseg_bn_bwd_apply": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp,
+                                    c_f, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "semseg_add_act": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
+    "semseg_scale_nc": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_f32_to_act": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_vp]),
+    "semseg_act_to_f32": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_ll, c_int, c_vp]),
+    "semseg_maxpool3x3s2_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_maxpool3x3s2_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_ppm_pool": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "semseg_ppm_pool_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp,
+                                    c_int, c_vp]),
+    "semseg_ppm_upsample_concat": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                                           c_int, c_vp, c_vp, c_int, c_vp]),
+    "semseg_ppm_upsample_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                                        c_vp]),
     "semseg_upsample_ce_workspace_floats": (c_ll, [c_int, c_int, c_int]),
     "semseg_upsample_ce_fwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp,
                                        c_vp, c_vp, c_vp, c_vp]),

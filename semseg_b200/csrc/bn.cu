@@ -5,6 +5,7 @@
 // (biased variance for normalisation, unbiased for running_var, eps 1e-5, momentum 0.1).
 #include "host_common.h"
 #include "ptx.cuh"
+#include "act.cuh"
 
 namespace sb {
 
@@ -302,9 +303,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // Grid sizing guarantees (gridDim.x * blockDim.x) % (C/8) == 0, so a thread keeps the same 8 channels for its
 // whole grid-stride loop and the per-channel coefficients are loaded once.
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch, const float* __restrict__ ss,
-                                const __nv_bfloat16* __restrict__ res, int res_pitch, __nv_bfloat16* __restrict__ y,
-                                int y_pitch, long long M, int C, int relu) {
+template <bool S>
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo, int x_pitch,
+                                const float* __restrict__ ss, const __nv_bfloat16* __restrict__ res,
+                                const __nv_bfloat16* __restrict__ res_lo, int res_pitch, __nv_bfloat16* __restrict__ y,
+                                __nv_bfloat16* __restrict__ y_lo, int y_pitch, long long M, int C, int relu) {
   const int groups = C >> 3;
   long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -320,47 +323,49 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_pitch
   long long p = idx / groups;
   constexpr int U = 4;
   for (; p + (U - 1) * pstride < M; p += U * pstride) {
-    uint4 xv[U], rv[U];
+    Raw8<S> xv[U], rv[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) xv[u] = *reinterpret_cast<const uint4*>(x + (p + u * pstride) * x_pitch + c0);
+    for (int u = 0; u < U; ++u) xv[u] = act_ldraw<S>(x, x_lo, (p + u * pstride) * x_pitch + c0);
     if (res) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) rv[u] = *reinterpret_cast<const uint4*>(res + (p + u * pstride) * res_pitch + c0);
+      for (int u = 0; u < U; ++u) rv[u] = act_ldraw<S>(res, res_lo, (p + u * pstride) * res_pitch + c0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float f[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      unpack8(xv[u], f);
-      if (res) unpack8(rv[u], r);
+      act_unpack<S>(xv[u], f);
+      if (res) act_unpack<S>(rv[u], r);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float v = fmaf(f[q], sc[q], sh[q]) + r[q];
         if (relu) v = fmaxf(v, 0.f);
         f[q] = v;
       }
-      *reinterpret_cast<uint4*>(y + (p + u * pstride) * y_pitch + c0) = pack8(f);
+      act_st8<S>(y, y_lo, (p + u * pstride) * y_pitch + c0, f);
     }
   }
   for (; p < M; p += pstride) {
     float f[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), f);
-    if (res) unpack8(*reinterpret_cast<const uint4*>(res + p * res_pitch + c0), r);
+    act_ld8<S>(x, x_lo, p * x_pitch + c0, f);
+    if (res) act_ld8<S>(res, res_lo, p * res_pitch + c0, r);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float v = fmaf(f[q], sc[q], sh[q]) + r[q];
       if (relu) v = fmaxf(v, 0.f);
       f[q] = v;
     }
-    *reinterpret_cast<uint4*>(y + p * y_pitch + c0) = pack8(f);
+    act_st8<S>(y, y_lo, p * y_pitch + c0, f);
   }
 }
 
 // Backward reduce, stage 1: per-chunk sums of dz and dz*xhat. block = 8 groups x 32 pixel lanes.
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pitch,
-                                     const __nv_bfloat16* __restrict__ y, int y_pitch,
-                                     const __nv_bfloat16* __restrict__ x, int x_pitch,
-                                     const float* __restrict__ mean_invstd, const float* __restrict__ ss, int M,
-                                     int C, int relu, int rows_per_chunk, float* __restrict__ part) {
+template <bool S>
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy_lo,
+                                     int dy_pitch, const __nv_bfloat16* __restrict__ y,
+                                     const __nv_bfloat16* __restrict__ y_lo, int y_pitch,
+                                     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo,
+                                     int x_pitch, const float* __restrict__ mean_invstd, const float* __restrict__ ss,
+                                     int M, int C, int relu, int rows_per_chunk, float* __restrict__ part) {
   __shared__ float s_a[32][65];
   __shared__ float s_b[32][65];
   const int gl = threadIdx.x & 7;
@@ -382,50 +387,9 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
     }
     const bool mask_from_y = relu && y != nullptr;
     const bool mask_from_x = relu && y == nullptr;
-    constexpr int U = 4;  // rows in flight per thread
-    int r = r0 + pl;
-    for (; r + (U - 1) * 32 < r1; r += U * 32) {
-      uint4 dv[U], xr[U], yr[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        dv[u] = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r + u * 32) * dy_pitch + c0);
-        xr[u] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r + u * 32) * x_pitch + c0);
-      }
+    constexpr int U = S ? 2 : 4;  // rows in flight per thread
+    auto accumulate = [&](float (&d)[8], const float (&xv)[8], const float (&yv)[8]) {
       if (mask_from_y) {
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          yr[u] = *reinterpret_cast<const uint4*>(y + static_cast<size_t>(r + u * 32) * y_pitch + c0);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float d[8], xv[8];
-        unpack8(dv[u], d);
-        unpack8(xr[u], xv);
-        if (mask_from_y) {
-          float yv[8];
-          unpack8(yr[u], yv);
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (!(yv[q] > 0.f)) d[q] = 0.f;
-        } else if (mask_from_x) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (!(fmaf(xv[q], msc[q], msh[q]) > 0.f)) d[q] = 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          a[q] += d[q];
-          b[q] = fmaf(d[q], (xv[q] - mean[q]) * invstd[q], b[q]);
-        }
-      }
-    }
-    for (; r < r1; r += 32) {
-      float d[8], xv[8];
-      unpack8(*reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * dy_pitch + c0), d);
-      unpack8(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * x_pitch + c0), xv);
-      if (mask_from_y) {
-        float yv[8];
-        unpack8(*reinterpret_cast<const uint4*>(y + static_cast<size_t>(r) * y_pitch + c0), yv);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           if (!(yv[q] > 0.f)) d[q] = 0.f;
@@ -439,6 +403,34 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int d
         a[q] += d[q];
         b[q] = fmaf(d[q], (xv[q] - mean[q]) * invstd[q], b[q]);
       }
+    };
+    int r = r0 + pl;
+    for (; r + (U - 1) * 32 < r1; r += U * 32) {
+      Raw8<S> dv[U], xr[U], yr[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        dv[u] = act_ldraw<S>(dy, dy_lo, static_cast<long long>(r + u * 32) * dy_pitch + c0);
+        xr[u] = act_ldraw<S>(x, x_lo, static_cast<long long>(r + u * 32) * x_pitch + c0);
+      }
+      if (mask_from_y) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) yr[u] = act_ldraw<S>(y, y_lo, static_cast<long long>(r + u * 32) * y_pitch + c0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float d[8], xv[8], yv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        act_unpack<S>(dv[u], d);
+        act_unpack<S>(xr[u], xv);
+        if (mask_from_y) act_unpack<S>(yr[u], yv);
+        accumulate(d, xv, yv);
+      }
+    }
+    for (; r < r1; r += 32) {
+      float d[8], xv[8], yv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      act_ld8<S>(dy, dy_lo, static_cast<long long>(r) * dy_pitch + c0, d);
+      act_ld8<S>(x, x_lo, static_cast<long long>(r) * x_pitch + c0, xv);
+      if (mask_from_y) act_ld8<S>(y, y_lo, static_cast<long long>(r) * y_pitch + c0, yv);
+      accumulate(d, xv, yv);
     }
   }
 #pragma unroll
@@ -490,14 +482,17 @@ __global__ void __launch_bounds__(1024) bn_bwd_reduce_final_kernel(const float* 
   }
 }
 
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pitch,
-                                    const __nv_bfloat16* __restrict__ y, int y_pitch,
-                                    const __nv_bfloat16* __restrict__ x, int x_pitch,
-                                    const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+template <bool S>
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy_lo,
+                                    int dy_pitch, const __nv_bfloat16* __restrict__ y,
+                                    const __nv_bfloat16* __restrict__ y_lo, int y_pitch,
+                                    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo,
+                                    int x_pitch, const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
                                     const float* __restrict__ ss, const float* __restrict__ sums, float inv_count,
-                                    long long M, int C, int relu,
-                                    __nv_bfloat16* __restrict__ dx, int dx_pitch, __nv_bfloat16* __restrict__ dres,
-                                    int dres_pitch, float* __restrict__ dgamma_dbeta) {
+                                    long long M, int C, int relu, __nv_bfloat16* __restrict__ dx,
+                                    __nv_bfloat16* __restrict__ dx_lo, int dx_pitch, __nv_bfloat16* __restrict__ dres,
+                                    __nv_bfloat16* __restrict__ dres_lo, int dres_pitch,
+                                    float* __restrict__ dgamma_dbeta) {
   const int groups = C >> 3;
   if (dgamma_dbeta && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -523,49 +518,8 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
     kx[q] = -ka[q] * invstd * sums[C + c] * inv_count;
     kb[q] = -ka[q] * sums[c] * inv_count - kx[q] * mean;
   }
-  const long long pstride = stride / groups;
-  long long p = idx / groups;
-  constexpr int U = 2;
-  for (; p + (U - 1) * pstride < M; p += U * pstride) {
-    uint4 dv[U], xr[U], yr[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      dv[u] = *reinterpret_cast<const uint4*>(dy + (p + u * pstride) * dy_pitch + c0);
-      xr[u] = *reinterpret_cast<const uint4*>(x + (p + u * pstride) * x_pitch + c0);
-    }
+  auto finish = [&](float (&d)[8], const float (&xv)[8], const float (&yv)[8], long long pp) {
     if (mask_from_y) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) yr[u] = *reinterpret_cast<const uint4*>(y + (p + u * pstride) * y_pitch + c0);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float d[8], xv[8], o[8];
-      unpack8(dv[u], d);
-      unpack8(xr[u], xv);
-      if (mask_from_y) {
-        float yv[8];
-        unpack8(yr[u], yv);
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (!(yv[q] > 0.f)) d[q] = 0.f;
-      } else if (mask_from_x) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (!(fmaf(xv[q], msc[q], msh[q]) > 0.f)) d[q] = 0.f;
-      }
-      if (dres) *reinterpret_cast<uint4*>(dres + (p + u * pstride) * dres_pitch + c0) = pack8(d);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) o[q] = fmaf(ka[q], d[q], fmaf(kx[q], xv[q], kb[q]));
-      *reinterpret_cast<uint4*>(dx + (p + u * pstride) * dx_pitch + c0) = pack8(o);
-    }
-  }
-  for (; p < M; p += pstride) {
-    float d[8], xv[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(dy + p * dy_pitch + c0), d);
-    unpack8(*reinterpret_cast<const uint4*>(x + p * x_pitch + c0), xv);
-    if (mask_from_y) {
-      float yv[8];
-      unpack8(*reinterpret_cast<const uint4*>(y + p * y_pitch + c0), yv);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         if (!(yv[q] > 0.f)) d[q] = 0.f;
@@ -574,34 +528,50 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy
       for (int q = 0; q < 8; ++q)
         if (!(fmaf(xv[q], msc[q], msh[q]) > 0.f)) d[q] = 0.f;
     }
-    if (dres) *reinterpret_cast<uint4*>(dres + p * dres_pitch + c0) = pack8(d);
+    if (dres) act_st8<S>(dres, dres_lo, pp * dres_pitch + c0, d);
+    float o[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) o[q] = fmaf(ka[q], d[q], fmaf(kx[q], xv[q], kb[q]));
-    *reinterpret_cast<uint4*>(dx + p * dx_pitch + c0) = pack8(o);
-  }
-}
-
-__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pitch,
-                                const __nv_bfloat16* __restrict__ y, int y_pitch, __nv_bfloat16* __restrict__ dz,
-                                int dz_pitch, long long M, int C) {
-  const int groups = C >> 3;
-  const long long total = M * groups;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long p = idx / groups;
-    const int c0 = static_cast<int>(idx - p * groups) << 3;
-    float d[8], yv[8];
-    unpack8(*reinterpret_cast<const uint4*>(dy + p * dy_pitch + c0), d);
-    unpack8(*reinterpret_cast<const uint4*>(y + p * y_pitch + c0), yv);
+    act_st8<S>(dx, dx_lo, pp * dx_pitch + c0, o);
+  };
+  const long long pstride = stride / groups;
+  long long p = idx / groups;
+  constexpr int U = 2;
+  for (; p + (U - 1) * pstride < M; p += U * pstride) {
+    Raw8<S> dv[U], xr[U], yr[U];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (!(yv[q] > 0.f)) d[q] = 0.f;
-    *reinterpret_cast<uint4*>(dz + p * dz_pitch + c0) = pack8(d);
+    for (int u = 0; u < U; ++u) {
+      dv[u] = act_ldraw<S>(dy, dy_lo, (p + u * pstride) * dy_pitch + c0);
+      xr[u] = act_ldraw<S>(x, x_lo, (p + u * pstride) * x_pitch + c0);
+    }
+    if (mask_from_y) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) yr[u] = act_ldraw<S>(y, y_lo, (p + u * pstride) * y_pitch + c0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float d[8], xv[8], yv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      act_unpack<S>(dv[u], d);
+      act_unpack<S>(xr[u], xv);
+      if (mask_from_y) act_unpack<S>(yr[u], yv);
+      finish(d, xv, yv, p + u * pstride);
+    }
+  }
+  for (; p < M; p += pstride) {
+    float d[8], xv[8], yv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    act_ld8<S>(dy, dy_lo, p * dy_pitch + c0, d);
+    act_ld8<S>(x, x_lo, p * x_pitch + c0, xv);
+    if (mask_from_y) act_ld8<S>(y, y_lo, p * y_pitch + c0, yv);
+    finish(d, xv, yv, p);
   }
 }
 
-__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, int a_pitch, const __nv_bfloat16* __restrict__ b,
-                                int b_pitch, __nv_bfloat16* __restrict__ out, int out_pitch, long long M, int C) {
+// out = a + b
+template <bool S>
+__global__ void add_act_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ a_lo, int a_pitch,
+                               const __nv_bfloat16* __restrict__ b, const __nv_bfloat16* __restrict__ b_lo, int b_pitch,
+                               __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, int out_pitch,
+                               long long M, int C) {
   const int groups = C >> 3;
   const long long total = M * groups;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -609,11 +579,143 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, int a_pitch
     const long long p = idx / groups;
     const int c0 = static_cast<int>(idx - p * groups) << 3;
     float x[8], z[8];
-    unpack8(*reinterpret_cast<const uint4*>(a + p * a_pitch + c0), x);
-    unpack8(*reinterpret_cast<const uint4*>(b + p * b_pitch + c0), z);
+    act_ld8<S>(a, a_lo, p * a_pitch + c0, x);
+    act_ld8<S>(b, b_lo, p * b_pitch + c0, z);
 #pragma unroll
     for (int q = 0; q < 8; ++q) x[q] += z[q];
-    *reinterpret_cast<uint4*>(out + p * out_pitch + c0) = pack8(x);
+    act_st8<S>(out, out_lo, p * out_pitch + c0, x);
+  }
+}
+
+// out[n, p, c] = x[n, p, c] * s[n, c]  (Dropout2d: one Bernoulli-derived factor per (image, channel)).
+template <bool S>
+__global__ void scale_nc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo, int x_pitch,
+                                const float* __restrict__ s, __nv_bfloat16* __restrict__ out,
+                                __nv_bfloat16* __restrict__ out_lo, int out_pitch, int N, long long HW, int C) {
+  const int groups = C >> 3;
+  const long long total = static_cast<long long>(N) * HW * groups;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = idx / groups;
+    const int c0 = static_cast<int>(idx - p * groups) << 3;
+    const int n = static_cast<int>(p / HW);
+    float f[8];
+    act_ld8<S>(x, x_lo, p * x_pitch + c0, f);
+    const float4 s0 = *reinterpret_cast<const float4*>(s + static_cast<size_t>(n) * C + c0);
+    const float4 s1 = *reinterpret_cast<const float4*>(s + static_cast<size_t>(n) * C + c0 + 4);
+    f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+    f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+    act_st8<S>(out, out_lo, p * out_pitch + c0, f);
+  }
+}
+
+// K-sliced conv finish: y = epilogue(sum_s partial[s]) for a chunk of pixels x 64 channels per block (8 channel groups
+// x 32 pixel lanes), plus the chunk's per-channel (sum, sum of squares, count) row in the conv-epilogue statistics format.
+template <bool S>
+__global__ void __launch_bounds__(256)
+conv_splitk_finish_kernel(const float* __restrict__ part, int k_slices, long long slice_stride, int part_pitch, int M, int C,
+                          int affine, int relu, const float* __restrict__ scale, const float* __restrict__ shift,
+                          const __nv_bfloat16* __restrict__ res, const __nv_bfloat16* __restrict__ res_lo, int res_pitch,
+                          __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y_lo, int y_pitch,
+                          int rows_per_chunk, float* __restrict__ stats) {
+  __shared__ float s_a[32][65];
+  __shared__ float s_b[32][65];
+  const int gl = threadIdx.x & 7;
+  const int pl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + gl * 8;
+  const int chunk = blockIdx.y;
+  const int r0 = chunk * rows_per_chunk;
+  const int r1 = min(M, r0 + rows_per_chunk);
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float sc[8], sh[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    sc[q] = (affine && scale) ? scale[c0 + q] : 1.f;
+    sh[q] = (affine && shift) ? shift[c0 + q] : 0.f;
+  }
+  for (int r = r0 + pl; r < r1; r += 32) {
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const float* src = part + static_cast<long long>(r) * part_pitch + c0;
+    for (int s = 0; s < k_slices; ++s) {   // fixed order, fp32 round-to-nearest adds
+      const float4 p0 = *reinterpret_cast<const float4*>(src + s * slice_stride);
+      const float4 p1 = *reinterpret_cast<const float4*>(src + s * slice_stride + 4);
+      v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+      v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+    }
+    if (affine) {
+      float rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (res) act_ld8<S>(res, res_lo, static_cast<long long>(r) * res_pitch + c0, rr);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float t = fmaf(v[q], sc[q], sh[q]) + rr[q];
+        v[q] = relu ? fmaxf(t, 0.f) : t;
+      }
+    }
+    act_st8<S>(y, y_lo, static_cast<long long>(r) * y_pitch + c0, v);
+    if (stats) {   // statistics of the values as stored (hi + lo / bf16), like the conv epilogue
+      float w[8];
+      act_ld8<S>(y, y_lo, static_cast<long long>(r) * y_pitch + c0, w);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        a[q] += w[q];
+        b[q] = fmaf(w[q], w[q], b[q]);
+      }
+    }
+  }
+  if (!stats) return;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    s_a[pl][gl * 8 + q] = a[q];
+    s_b[pl][gl * 8 + q] = b[q];
+  }
+  __syncthreads();
+  if (pl < 3) {
+    float* row = stats + static_cast<size_t>(chunk) * 3 * C;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float t = 0.f;
+      if (pl < 2) {
+        float(*src)[65] = pl == 0 ? s_a : s_b;
+        for (int i = 0; i < 32; ++i) t += src[i][gl * 8 + q];
+      } else {
+        t = static_cast<float>(r1 - r0);
+      }
+      row[pl * C + c0 + q] = t;
+    }
+  }
+}
+
+// fp32 [M][in_pitch] (first C columns) -> activation [M][out_pitch] with columns C..Cp-1 zero filled (Cp % 8 == 0).
+template <bool S>
+__global__ void f32_to_act_kernel(const float* __restrict__ in, int in_pitch, __nv_bfloat16* __restrict__ out,
+                                  __nv_bfloat16* __restrict__ out_lo, int out_pitch, long long M, int C, int Cp) {
+  const int groups = Cp >> 3;
+  const long long total = M * groups;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = idx / groups;
+    const int c0 = static_cast<int>(idx - p * groups) << 3;
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = (c0 + q < C) ? in[p * in_pitch + c0 + q] : 0.f;
+    act_st8<S>(out, out_lo, p * out_pitch + c0, f);
+  }
+}
+
+// activation [M][in_pitch] -> fp32 [M][out_pitch] (C % 8 == 0 columns).
+template <bool S>
+__global__ void act_to_f32_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ in_lo,
+                                  int in_pitch, float* __restrict__ out, int out_pitch, long long M, int C) {
+  const int groups = C >> 3;
+  const long long total = M * groups;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = idx / groups;
+    const int c0 = static_cast<int>(idx - p * groups) << 3;
+    float f[8];
+    act_ld8<S>(in, in_lo, p * in_pitch + c0, f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) out[p * out_pitch + c0 + q] = f[q];
   }
 }
 
@@ -628,6 +730,7 @@ struct PeerArgs {
   unsigned* counter;    // local block-arrival counter (self-resetting)
   int world, rank, slot, slot_floats;
   unsigned seq;         // strictly increasing per training step
+  long long timeout_ticks;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
@@ -644,30 +747,44 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
   return v;
 }
 
-// Called by every thread of every block after the block's own data has been stored to buf[rank].
-__device__ __forceinline__ void peer_publish_and_wait(const PeerArgs& pa) {
+// Spin limit of the cross-rank wait in clock64 ticks (~2 GHz): default 10 minutes, like a collective library's watchdog
+// (a debugger, a host stall or a straggler on one rank must not kill the other ranks' CUDA contexts after seconds);
+// SEMSEG_B200_P2P_TIMEOUT_S overrides it. Set by the host wrappers through PeerArgs::timeout_ticks.
+//
+// Exchange protocol (called by every thread of every block after the block's own data has been stored to buf[rank]):
+// every block counts itself in; ONLY THE LAST block of this rank's grid goes on — it raises this rank's flag in every
+// peer's flag array, waits for the peers' flags and returns true; all other blocks return false and exit. So exactly one
+// block per rank ever spins: no co-residency requirement between the blocks of the grid, and nothing that an NCCL kernel
+// sharing the SMs could dead-lock with. The caller's last block then does the cross-rank merge for ALL
+// channels (a few thousand values, over NVLink).
+__device__ __forceinline__ bool peer_publish_and_wait(const PeerArgs& pa) {
+  __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence_system();                       // my block's stores to buf[rank] are visible system-wide ...
     const unsigned prev = atomicAdd(pa.counter, 1u);
-    if (prev == gridDim.x - 1) {  // last block of this rank: everything is published
-      *pa.counter = 0u;
-      __threadfence_system();
-      for (int p = 0; p < pa.world; ++p) st_release_sys(pa.flags[p] + pa.slot * pa.world + pa.rank, pa.seq);
-    }
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;     // ... before the last arriver publishes the flag
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  if (threadIdx.x == 0) {
+    *pa.counter = 0u;
+    __threadfence_system();
+    for (int p = 0; p < pa.world; ++p) st_release_sys(pa.flags[p] + pa.slot * pa.world + pa.rank, pa.seq);
   }
   if (threadIdx.x < pa.world) {
     const unsigned* f = pa.flags[pa.rank] + pa.slot * pa.world + threadIdx.x;
     const long long t0 = clock64();
     while (ld_acquire_sys(f) != pa.seq) {
-      if (clock64() - t0 > 8000000000LL) {  // a missing peer must not hang the GPU
-        printf("semseg_b200: SyncBN peer exchange timed out (rank %d waiting for rank %d, slot %d)\n", pa.rank,
-               static_cast<int>(threadIdx.x), pa.slot);
+      if (clock64() - t0 > pa.timeout_ticks) {  // a peer that never arrives must not hang the GPU forever
+        printf("semseg_b200: SyncBN peer exchange timed out (rank %d waiting for rank %d, slot %d, seq %u)\n", pa.rank,
+               static_cast<int>(threadIdx.x), pa.slot, pa.seq);
         __trap();
       }
     }
   }
   __syncthreads();
+  return true;
 }
 
 // Forward: merge this rank's conv partials, exchange (mean, M2, n), merge over ranks, finalise.
@@ -678,17 +795,17 @@ __global__ void __launch_bounds__(1024) bn_finalize_p2p_kernel(const float* __re
                                        float* __restrict__ mean_invstd, float* __restrict__ scale_shift, PeerArgs pa) {
   __shared__ Moments sm[32][CH + 1];
   const Moments own_m = block_conv_moments<CH>(part, T, C, blockIdx.x * CH, sm);
-  const int c = blockIdx.x * CH + (threadIdx.x >> 5);
-  const bool fin = (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < CH && c < C;  // this thread finishes channel c
+  const int c_own = blockIdx.x * CH + (threadIdx.x >> 5);
   const size_t off = static_cast<size_t>(pa.slot) * pa.slot_floats;
-  if (fin) {
+  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < CH && c_own < C) {
     float* own = pa.buf[pa.rank] + off;
-    own[c] = own_m.mean;
-    own[C + c] = own_m.m2;
-    own[2 * C + c] = own_m.n;
+    own[c_own] = own_m.mean;
+    own[C + c_own] = own_m.m2;
+    own[2 * C + c_own] = own_m.n;
   }
-  peer_publish_and_wait(pa);
-  if (fin) {
+  if (!peer_publish_and_wait(pa)) return;
+  // last block of this rank: every rank's (mean, M2, n) block is published -> merge in rank order and finalise all channels
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     Moments r = {0.f, 0.f, 0.f};
     for (int p = 0; p < pa.world; ++p) {
       const float* b = pa.buf[p] + off;
@@ -746,11 +863,11 @@ __global__ void __launch_bounds__(1024) bn_bwd_reduce_final_p2p_kernel(const flo
     sums_local[idx] = r;
     pa.buf[pa.rank][off + idx] = r;
   }
-  peer_publish_and_wait(pa);
-  if (tl == 0 && idx < 2 * C) {
+  if (!peer_publish_and_wait(pa)) return;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {   // last block: all ranks published -> totals for every channel
     float r = 0.f;
-    for (int p = 0; p < pa.world; ++p) r += ld_relaxed_sys(pa.buf[p] + off + idx);
-    sums_total[idx] = r;
+    for (int p = 0; p < pa.world; ++p) r += ld_relaxed_sys(pa.buf[p] + off + i);
+    sums_total[i] = r;
   }
 }
 
@@ -856,90 +973,182 @@ extern "C" int semseg_bn_fold_eval(const float* gamma, const float* beta, const 
   return SEMSEG_OK;
 }
 
-extern "C" int semseg_bn_apply(const void* x, int x_pitch, const float* scale_shift, const void* residual,
-                               int res_pitch, void* y, int y_pitch, int M, int C, int relu, void* stream_) {
+extern "C" int semseg_bn_apply(const void* x, const void* x_lo, int x_pitch, const float* scale_shift,
+                               const void* residual, const void* residual_lo, int res_pitch, void* y, void* y_lo,
+                               int y_pitch, int M, int C, int relu, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(x && scale_shift && y && M > 0 && C > 0, "bn_apply: bad args");
   SB_CHECK_ARG(C % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && (!residual || res_pitch % 8 == 0),
                "bn_apply: channels and pitches must be multiples of 8");
+  const bool split = x_lo != nullptr;
+  SB_CHECK_ARG((y_lo != nullptr) == split && (!residual || (residual_lo != nullptr) == split),
+               "bn_apply: all tensors must use the same storage form (plain or split)");
   const long long total = static_cast<long long>(M) * (C / 8);
-  bn_apply_kernel<<<ew_grid_fixed_channels(total, 256, C / 8), 256, 0, stream>>>(static_cast<const bf16*>(x), x_pitch, scale_shift,
-                                                           static_cast<const bf16*>(residual), res_pitch,
-                                                           static_cast<bf16*>(y), y_pitch, M, C, relu);
+  const int grid = ew_grid_fixed_channels(total, 256, C / 8);
+  SB_ACT_DISPATCH(split, bn_apply_kernel<kS><<<grid, 256, 0, stream>>>(
+                             static_cast<const bf16*>(x), static_cast<const bf16*>(x_lo), x_pitch, scale_shift,
+                             static_cast<const bf16*>(residual), static_cast<const bf16*>(residual_lo), res_pitch,
+                             static_cast<bf16*>(y), static_cast<bf16*>(y_lo), y_pitch, M, C, relu));
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
 
-extern "C" int semseg_bn_bwd_reduce(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x,
-                                    int x_pitch, const float* mean_invstd, const float* scale_shift, int M, int C,
-                                    int relu, float* workspace,
-                                    long long workspace_floats, float* sums, void* stream_) {
+static int launch_bwd_reduce(const void* dy, const void* dy_lo, int dy_pitch, const void* y, const void* y_lo,
+                             int y_pitch, const void* x, const void* x_lo, int x_pitch, const float* mean_invstd,
+                             const float* scale_shift, int M, int C, int relu, float* workspace, cudaStream_t stream) {
+  const bool split = dy_lo != nullptr;
+  SB_CHECK_ARG((x_lo != nullptr) == split && (!(relu && y) || (y_lo != nullptr) == split),
+               "bn_bwd_reduce: all tensors must use the same storage form (plain or split)");
+  const int rows = chunk_rows(M);
+  const int chunks = cdiv(M, rows);
+  dim3 grid(cdiv(C, 64), chunks);
+  SB_ACT_DISPATCH(split, bn_bwd_reduce_kernel<kS><<<grid, 256, 0, stream>>>(
+                             static_cast<const bf16*>(dy), static_cast<const bf16*>(dy_lo), dy_pitch,
+                             static_cast<const bf16*>(y), static_cast<const bf16*>(y_lo), y_pitch,
+                             static_cast<const bf16*>(x), static_cast<const bf16*>(x_lo), x_pitch, mean_invstd,
+                             scale_shift, M, C, relu, rows, workspace));
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_bn_bwd_reduce(const void* dy, const void* dy_lo, int dy_pitch, const void* y, const void* y_lo,
+                                    int y_pitch, const void* x, const void* x_lo, int x_pitch,
+                                    const float* mean_invstd, const float* scale_shift, int M, int C, int relu,
+                                    float* workspace, long long workspace_floats, float* sums, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(dy && x && mean_invstd && workspace && sums && M > 0 && C > 0, "bn_bwd_reduce: bad args");
   SB_CHECK_ARG(!relu || y || scale_shift, "bn_bwd_reduce: relu needs y or scale_shift");
   SB_CHECK_ARG(C % 8 == 0 && dy_pitch % 8 == 0 && x_pitch % 8 == 0 && (!(relu && y) || y_pitch % 8 == 0),
                "bn_bwd_reduce: channels and pitches must be multiples of 8");
   SB_CHECK_ARG(workspace_floats >= semseg_bn_workspace_floats(M, C), "bn_bwd_reduce: workspace too small");
-  const int rows = chunk_rows(M);
-  const int chunks = cdiv(M, rows);
-  dim3 grid(cdiv(C, 64), chunks);
-  bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_pitch, static_cast<const bf16*>(y),
-                                                 y_pitch, static_cast<const bf16*>(x), x_pitch, mean_invstd,
-                                                 scale_shift, M, C, relu, rows, workspace);
-  SB_LAUNCHED();
-  bn_bwd_reduce_final_kernel<<<cdiv(2 * C, 32), 1024, 0, stream>>>(workspace, chunks, C, sums);
+  int r = launch_bwd_reduce(dy, dy_lo, dy_pitch, y, y_lo, y_pitch, x, x_lo, x_pitch, mean_invstd, scale_shift, M, C,
+                            relu, workspace, stream);
+  if (r) return r;
+  bn_bwd_reduce_final_kernel<<<cdiv(2 * C, 32), 1024, 0, stream>>>(workspace, cdiv(M, chunk_rows(M)), C, sums);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
 
-extern "C" int semseg_bn_bwd_apply(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x,
-                                   int x_pitch, const float* mean_invstd, const float* gamma,
-                                   const float* scale_shift, const float* sums,
-                                   float count, int M, int C, int relu, void* dx, int dx_pitch, void* dres,
-                                   int dres_pitch, float* dgamma_dbeta, void* stream_) {
+extern "C" int semseg_bn_bwd_apply(const void* dy, const void* dy_lo, int dy_pitch, const void* y, const void* y_lo,
+                                   int y_pitch, const void* x, const void* x_lo, int x_pitch,
+                                   const float* mean_invstd, const float* gamma, const float* scale_shift,
+                                   const float* sums, float count, int M, int C, int relu, void* dx, void* dx_lo,
+                                   int dx_pitch, void* dres, void* dres_lo, int dres_pitch, float* dgamma_dbeta,
+                                   void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(dy && x && mean_invstd && sums && dx && M > 0 && C > 0 && count > 0.f, "bn_bwd_apply: bad args");
   SB_CHECK_ARG(!relu || y || scale_shift, "bn_bwd_apply: relu needs y or scale_shift");
   SB_CHECK_ARG(C % 8 == 0 && dy_pitch % 8 == 0 && x_pitch % 8 == 0 && dx_pitch % 8 == 0 &&
                    (!(relu && y) || y_pitch % 8 == 0) && (!dres || dres_pitch % 8 == 0),
                "bn_bwd_apply: channels and pitches must be multiples of 8");
+  const bool split = dy_lo != nullptr;
+  SB_CHECK_ARG((x_lo != nullptr) == split && (dx_lo != nullptr) == split &&
+                   (!(relu && y) || (y_lo != nullptr) == split) && (!dres || (dres_lo != nullptr) == split),
+               "bn_bwd_apply: all tensors must use the same storage form (plain or split)");
   const long long total = static_cast<long long>(M) * (C / 8);
-  bn_bwd_apply_kernel<<<ew_grid_fixed_channels(total, 256, C / 8), 256, 0, stream>>>(
-      static_cast<const bf16*>(dy), dy_pitch, static_cast<const bf16*>(y), y_pitch, static_cast<const bf16*>(x),
-      x_pitch, mean_invstd, gamma, scale_shift, sums, 1.f / count, M, C, relu, static_cast<bf16*>(dx), dx_pitch,
-      static_cast<bf16*>(dres), dres_pitch, dgamma_dbeta);
+  const int grid = ew_grid_fixed_channels(total, 256, C / 8);
+  SB_ACT_DISPATCH(split, bn_bwd_apply_kernel<kS><<<grid, 256, 0, stream>>>(
+                             static_cast<const bf16*>(dy), static_cast<const bf16*>(dy_lo), dy_pitch,
+                             static_cast<const bf16*>(y), static_cast<const bf16*>(y_lo), y_pitch,
+                             static_cast<const bf16*>(x), static_cast<const bf16*>(x_lo), x_pitch, mean_invstd, gamma,
+                             scale_shift, sums, 1.f / count, M, C, relu, static_cast<bf16*>(dx),
+                             static_cast<bf16*>(dx_lo), dx_pitch, static_cast<bf16*>(dres),
+                             static_cast<bf16*>(dres_lo), dres_pitch, dgamma_dbeta));
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
 
-extern "C" int semseg_relu_bwd(const void* dy, int dy_pitch, const void* y, int y_pitch, void* dz, int dz_pitch,
-                               int M, int C, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SB_CHECK_ARG(dy && y && dz && M > 0 && C > 0 && C % 8 == 0 && dy_pitch % 8 == 0 && y_pitch % 8 == 0 &&
-                   dz_pitch % 8 == 0,
-               "relu_bwd: bad args");
-  const long long total = static_cast<long long>(M) * (C / 8);
-  relu_bwd_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_pitch,
-                                                           static_cast<const bf16*>(y), y_pitch,
-                                                           static_cast<bf16*>(dz), dz_pitch, M, C);
-  SB_LAUNCHED();
-  return SEMSEG_OK;
-}
-
-extern "C" int semseg_add_bf16(const void* a, int a_pitch, const void* b, int b_pitch, void* out, int out_pitch,
-                               int M, int C, void* stream_) {
+extern "C" int semseg_add_act(const void* a, const void* a_lo, int a_pitch, const void* b, const void* b_lo,
+                              int b_pitch, void* out, void* out_lo, int out_pitch, int M, int C, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(a && b && out && M > 0 && C > 0 && C % 8 == 0 && a_pitch % 8 == 0 && b_pitch % 8 == 0 &&
                    out_pitch % 8 == 0,
-               "add_bf16: bad args");
+               "add_act: bad args");
+  const bool split = a_lo != nullptr;
+  SB_CHECK_ARG((b_lo != nullptr) == split && (out_lo != nullptr) == split,
+               "add_act: all tensors must use the same storage form (plain or split)");
   const long long total = static_cast<long long>(M) * (C / 8);
-  add_bf16_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(a), a_pitch,
-                                                           static_cast<const bf16*>(b), b_pitch,
-                                                           static_cast<bf16*>(out), out_pitch, M, C);
+  SB_ACT_DISPATCH(split, add_act_kernel<kS><<<ew_grid(total, 256), 256, 0, stream>>>(
+                             static_cast<const bf16*>(a), static_cast<const bf16*>(a_lo), a_pitch,
+                             static_cast<const bf16*>(b), static_cast<const bf16*>(b_lo), b_pitch,
+                             static_cast<bf16*>(out), static_cast<bf16*>(out_lo), out_pitch, M, C));
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
 
+extern "C" int semseg_scale_nc(const void* x, const void* x_lo, int x_pitch, const float* scale, void* out,
+                               void* out_lo, int out_pitch, int N, int HW, int C, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(x && scale && out && N > 0 && HW > 0 && C > 0 && C % 8 == 0 && x_pitch % 8 == 0 && out_pitch % 8 == 0,
+               "scale_nc: bad args");
+  const bool split = x_lo != nullptr;
+  SB_CHECK_ARG((out_lo != nullptr) == split, "scale_nc: input and output must use the same storage form");
+  const long long total = static_cast<long long>(N) * HW * (C / 8);
+  SB_ACT_DISPATCH(split, scale_nc_kernel<kS><<<ew_grid(total, 256), 256, 0, stream>>>(
+                             static_cast<const bf16*>(x), static_cast<const bf16*>(x_lo), x_pitch, scale,
+                             static_cast<bf16*>(out), static_cast<bf16*>(out_lo), out_pitch, N, HW, C));
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+static int splitk_chunk_rows(int M) {
+  int rows = cdiv(M, 2048);
+  if (rows < 128) rows = 128;
+  return (rows + 31) & ~31;
+}
+
+extern "C" int semseg_conv_splitk_rows(int M) { return M > 0 ? cdiv(M, splitk_chunk_rows(M)) : SEMSEG_E_INVALID; }
+
+extern "C" int semseg_conv_splitk_finish(const float* partial, int k_slices, long long slice_stride, int part_pitch,
+                                         int M, int C, int epi_mode, int relu, const float* scale, const float* shift,
+                                         const void* residual, const void* residual_lo, int res_pitch, void* y,
+                                         void* y_lo, int y_pitch, float* stats_partial, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(partial && y && k_slices >= 1 && M > 0 && C > 0 && C % 64 == 0, "conv_splitk_finish: bad args");
+  SB_CHECK_ARG(part_pitch % 4 == 0 && part_pitch >= C && slice_stride % 4 == 0 && y_pitch % 8 == 0 &&
+                   (!residual || res_pitch % 8 == 0),
+               "conv_splitk_finish: pitches must keep 16-byte alignment");
+  SB_CHECK_ARG(epi_mode == SEMSEG_EPI_RAW || epi_mode == SEMSEG_EPI_AFFINE, "conv_splitk_finish: RAW or AFFINE only");
+  SB_CHECK_ARG(!stats_partial || epi_mode == SEMSEG_EPI_RAW, "conv_splitk_finish: statistics only in RAW mode");
+  const bool split = y_lo != nullptr;
+  SB_CHECK_ARG(!residual || (residual_lo != nullptr) == split, "conv_splitk_finish: residual / y storage forms differ");
+  const int rows = splitk_chunk_rows(M);
+  dim3 grid(C / 64, cdiv(M, rows));
+  SB_ACT_DISPATCH(split, conv_splitk_finish_kernel<kS><<<grid, 256, 0, stream>>>(
+                             partial, k_slices, slice_stride, part_pitch, M, C, epi_mode == SEMSEG_EPI_AFFINE ? 1 : 0,
+                             relu, scale, shift, static_cast<const bf16*>(residual),
+                             static_cast<const bf16*>(residual_lo), res_pitch, static_cast<bf16*>(y),
+                             static_cast<bf16*>(y_lo), y_pitch, rows, stats_partial));
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_f32_to_act(const float* in, int in_pitch, void* out, void* out_lo, int out_pitch, long long M,
+                                 int C, int Cp, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(in && out && M > 0 && C > 0 && Cp >= C && Cp % 8 == 0 && out_pitch % 8 == 0 && out_pitch >= Cp &&
+                   in_pitch >= C,
+               "f32_to_act: bad args");
+  const long long total = M * (Cp / 8);
+  SB_ACT_DISPATCH(out_lo != nullptr, f32_to_act_kernel<kS><<<ew_grid(total, 256), 256, 0, stream>>>(
+                                         in, in_pitch, static_cast<bf16*>(out), static_cast<bf16*>(out_lo), out_pitch,
+                                         M, C, Cp));
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
+
+extern "C" int semseg_act_to_f32(const void* in, const void* in_lo, int in_pitch, float* out, int out_pitch,
+                                 long long M, int C, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SB_CHECK_ARG(in && out && M > 0 && C > 0 && C % 8 == 0 && in_pitch % 8 == 0 && out_pitch >= C,
+               "act_to_f32: bad args");
+  const long long total = M * (C / 8);
+  SB_ACT_DISPATCH(in_lo != nullptr, act_to_f32_kernel<kS><<<ew_grid(total, 256), 256, 0, stream>>>(
+                                        static_cast<const bf16*>(in), static_cast<const bf16*>(in_lo), in_pitch, out,
+                                        out_pitch, M, C));
+  SB_LAUNCHED();
+  return SEMSEG_OK;
+}
 
 static int fill_peer_args(sb::PeerArgs* pa, void* const* peer_bufs, void* const* peer_flags, void* counter, int world,
                           int rank, int slot, int slot_floats, unsigned seq, int need_floats) {
@@ -958,6 +1167,14 @@ static int fill_peer_args(sb::PeerArgs* pa, void* const* peer_bufs, void* const*
   pa->slot = slot;
   pa->slot_floats = slot_floats;
   pa->seq = seq;
+  static long long ticks = 0;
+  if (ticks == 0) {
+    const char* e = getenv("SEMSEG_B200_P2P_TIMEOUT_S");
+    double sec = e ? atof(e) : 600.0;
+    if (!(sec > 0.0)) sec = 600.0;
+    ticks = static_cast<long long>(sec * 2.0e9);
+  }
+  pa->timeout_ticks = ticks;
   return SEMSEG_OK;
 }
 
@@ -980,9 +1197,10 @@ extern "C" int semseg_bn_finalize_p2p(const float* stats_partial, int rows, int 
   return SEMSEG_OK;
 }
 
-extern "C" int semseg_bn_bwd_reduce_p2p(const void* dy, int dy_pitch, const void* y, int y_pitch, const void* x,
-                                        int x_pitch, const float* mean_invstd, const float* scale_shift, int M, int C,
-                                        int relu, float* workspace, long long workspace_floats, float* sums_local,
+extern "C" int semseg_bn_bwd_reduce_p2p(const void* dy, const void* dy_lo, int dy_pitch, const void* y,
+                                        const void* y_lo, int y_pitch, const void* x, const void* x_lo, int x_pitch,
+                                        const float* mean_invstd, const float* scale_shift, int M, int C, int relu,
+                                        float* workspace, long long workspace_floats, float* sums_local,
                                         float* sums_total, void* const* peer_bufs, void* const* peer_flags,
                                         void* counter, int world, int rank, int slot, int slot_floats, unsigned seq,
                                         void* stream_) {
@@ -996,15 +1214,11 @@ extern "C" int semseg_bn_bwd_reduce_p2p(const void* dy, int dy_pitch, const void
   sb::PeerArgs pa;
   int r = fill_peer_args(&pa, peer_bufs, peer_flags, counter, world, rank, slot, slot_floats, seq, 2 * C);
   if (r) return r;
-  const int rows = chunk_rows(M);
-  const int chunks = cdiv(M, rows);
-  dim3 grid(cdiv(C, 64), chunks);
-  bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_pitch, static_cast<const bf16*>(y),
-                                                 y_pitch, static_cast<const bf16*>(x), x_pitch, mean_invstd,
-                                                 scale_shift, M, C, relu, rows, workspace);
-  SB_LAUNCHED();
-  bn_bwd_reduce_final_p2p_kernel<<<cdiv(2 * C, 32), 1024, 0, stream>>>(workspace, chunks, C, sums_local, sums_total,
-                                                                      pa);
+  r = launch_bwd_reduce(dy, dy_lo, dy_pitch, y, y_lo, y_pitch, x, x_lo, x_pitch, mean_invstd, scale_shift, M, C, relu,
+                        workspace, stream);
+  if (r) return r;
+  bn_bwd_reduce_final_p2p_kernel<<<cdiv(2 * C, 32), 1024, 0, stream>>>(workspace, cdiv(M, chunk_rows(M)), C,
+                                                                      sums_local, sums_total, pa);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }

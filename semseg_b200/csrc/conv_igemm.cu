@@ -56,7 +56,15 @@ struct ConvKParams {
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
+  const __nv_bfloat16* residual_lo;  // split storage: lo plane of the residual
   int res_pitch;
+  int nseg;  // operand segments per K block: 1 = bf16, 3 = bf16x3 (x_hi*w_hi, x_lo*w_hi, x_hi*w_lo)
+  // K slicing (F32 epilogue only): work item = (pixel tile, channel tile, K slice); slice s accumulates K blocks
+  // [s*kb_per_slice, (s+1)*kb_per_slice) and writes its fp32 partial to out_f32 + s*slice_stride. Bounds the length of
+  // one tensor-core accumulation chain: tcgen05 accumulates in fp32 with truncation, a bias of ~2^-24 per MMA step
+  // towards zero (tools/probe_accum.py), negligible for bf16 but not at the 1e-5 level the bf16x3 mode works at.
+  int k_slices, kb_per_slice;
+  long long slice_stride;
   float* out_f32;
   int out_pitch;
   float* stats_partial;  // [gridDim.x * 4][3][Cout]: per epilogue warp (sum, sum of squares, count) per channel
@@ -69,10 +77,18 @@ struct ConvKParams {
 // BLOCK_N=256) and the freed smem buys more pipeline stages. TMA completions of both CTAs are credited to the leader's
 // full barrier; the leader's tcgen05.commit is multicast to both CTAs' empty / tmem_full barriers; the peer's epilogue
 // hands its accumulator stage back by arriving on the leader's tmem_empty barrier.
-template <int BLOCK_N, bool kCluster, int kEpiGroups>
+//
+// kSplit (bf16x3 operand mode, activations stored as hi/lo bf16 planes — act.cuh): every K block is issued three times,
+// (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo), into the same fp32 TMEM accumulator; the producer just picks the hi or lo
+// tensor map per segment, the MMA warp is unchanged. The epilogue splits its fp32 result into (hi, lo) again and stores
+// both planes (two staging tiles, two TMA stores); BatchNorm statistics are taken from hi + lo.
+template <int BLOCK_N, bool kCluster, int kEpiGroups, bool kSplit>
 __global__ void __launch_bounds__(conv_threads(kEpiGroups), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmC, const ConvKParams p) {
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmC_lo,
+                  const ConvKParams p) {
+  static_assert(!kSplit || kEpiGroups == 1, "split storage uses both staging buffers of the single epilogue group");
   using Cfg = ConvCfg<BLOCK_N>;
   constexpr int kNumThreads = conv_threads(kEpiGroups);
   constexpr int kEpiThreads = kEpiGroups * kEpiGroupThreads;
@@ -84,8 +100,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // Work items: (pixel tile, channel tile) or, clustered, (pair of pixel tiles, channel tile) per cluster.
   const int item_first = kCluster ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int item_step = kCluster ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int num_items = (kCluster ? ((p.num_m_tiles + 1) >> 1) : p.num_m_tiles) * p.n_tiles;
-  auto decode_item = [&](int item, int& m_tile, int& n_tile) -> bool {
+  const int num_items = (kCluster ? ((p.num_m_tiles + 1) >> 1) : p.num_m_tiles) * p.n_tiles * p.k_slices;
+  auto decode_item = [&](int item, int& m_tile, int& n_tile, int& k_slice) -> bool {
+    k_slice = item % p.k_slices;
+    item /= p.k_slices;
     n_tile = item % p.n_tiles;
     const int mi = item / p.n_tiles;
     const int m_raw = kCluster ? 2 * mi + static_cast<int>(cta_rank) : mi;
@@ -107,7 +125,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = p.taps * p.k_chunks;
+  const int nseg = kSplit ? p.nseg : 1;
+  const int total_kblk = p.taps * p.k_chunks;   // K blocks = (64-channel block, tap) pairs
+  auto slice_range = [&](int k_slice, int& kblk0, int& kblk1) {
+    kblk0 = k_slice * p.kb_per_slice;
+    kblk1 = min(kblk0 + p.kb_per_slice, total_kblk);
+  };
   const uint32_t a_bytes = static_cast<uint32_t>(p.bh * p.bw) * 128u;
   // bytes credited to a full barrier per stage: own A + whole B, or (pair mode, leader's barrier) both A tiles + both B halves
   const uint32_t stage_tx = (kCluster ? 2u * a_bytes : a_bytes) + static_cast<uint32_t>(Cfg::kBTileBytes);
@@ -116,6 +139,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
+    if (kSplit) {
+      tma_prefetch_desc(&tmA_lo);
+      tma_prefetch_desc(&tmB_lo);
+      tma_prefetch_desc(&tmC_lo);
+    }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -145,39 +173,44 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (elect_one()) {
       int it = 0;
       for (int item = item_first; item < num_items; item += item_step) {
-        int m_tile, n_tile;
-        decode_item(item, m_tile, n_tile);
+        int m_tile, n_tile, k_slice, kblk0, kblk1;
+        decode_item(item, m_tile, n_tile, k_slice);
+        slice_range(k_slice, kblk0, kblk1);
         const int tiles_per_img = p.tiles_h * p.tiles_w;
         const int img = m_tile / tiles_per_img;
         const int rem = m_tile - img * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.bh;
         const int w0 = (rem % p.tiles_w) * p.bw;
         const int n0 = n_tile * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kblk0 * nseg; kb < kblk1 * nseg; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t par = (it / kStages) & 1;
           mbar_wait(&empty_bar[s], par ^ 1);
-          const int cb = kb / p.taps;
-          const int t = kb - cb * p.taps;
+          const int ks = kb / nseg;          // (channel block, tap)
+          const int seg = kb - ks * nseg;    // 0: x_hi*w_hi, 1: x_lo*w_hi, 2: x_hi*w_lo
+          const int cb = ks / p.taps;
+          const int t = ks - cb * p.taps;
+          const CUtensorMap* mA = (kSplit && seg == 1) ? &tmA_lo : &tmA;
+          const CUtensorMap* mB = (kSplit && seg == 2) ? &tmB_lo : &tmB;
           uint8_t* a_dst = stage_base + s * kStageBytes;
           uint8_t* b_dst = a_dst + kATileBytes;
           if (kCluster) {
             // both CTAs' loads complete on the LEADER's full barrier; only the leader arms it
             const uint32_t lead_bar = mapa_u32(&full_bar[s], 0);
             if (is_leader) mbar_expect_tx(&full_bar[s], stage_tx);
-            tma_load_4d_2sm(a_dst, &tmA, lead_bar, cb * kBlockK, w0 + p.dw[t], h0 + p.dh[t],
+            tma_load_4d_2sm(a_dst, mA, lead_bar, cb * kBlockK, w0 + p.dw[t], h0 + p.dh[t],
                             img * p.img_mul + p.img_add[t]);
-            tma_load_3d_2sm(b_dst, &tmB, lead_bar, cb * kBlockK, n0 + static_cast<int>(cta_rank) * (BLOCK_N / 2),
+            tma_load_3d_2sm(b_dst, mB, lead_bar, cb * kBlockK, n0 + static_cast<int>(cta_rank) * (BLOCK_N / 2),
                             p.wtap[t]);
           } else {
             mbar_expect_tx(&full_bar[s], stage_tx);
-            tma_load_4d(a_dst, &tmA, &full_bar[s], cb * kBlockK, w0 + p.dw[t], h0 + p.dh[t],
+            tma_load_4d(a_dst, mA, &full_bar[s], cb * kBlockK, w0 + p.dw[t], h0 + p.dh[t],
                         img * p.img_mul + p.img_add[t]);
             // 3-D weights [taps][rows][cols]: coordinates (k, row, tap)
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
                 "%5}], [%2];" ::"r"(smem_u32(b_dst)),
-                "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[s])), "r"(cb * kBlockK), "r"(n0),
+                "l"(reinterpret_cast<uint64_t>(mB)), "r"(smem_u32(&full_bar[s])), "r"(cb * kBlockK), "r"(n0),
                 "r"(p.wtap[t])
                 : "memory");
           }
@@ -196,6 +229,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&tmem_empty[as], apar ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BLOCK_N);
+        int kblk0, kblk1;
+        slice_range((item % p.k_slices), kblk0, kblk1);
+        const int num_kb = (kblk1 - kblk0) * nseg;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t par = (it / kStages) & 1;
@@ -234,8 +270,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int tile_iter = 0;
     int store_buf = 0;
     for (int item = item_first; item < num_items; item += item_step, ++tile_iter) {
-      int m_tile, n_tile;
-      const bool tile_live = decode_item(item, m_tile, n_tile);
+      int m_tile, n_tile, k_slice;
+      const bool tile_live = decode_item(item, m_tile, n_tile, k_slice);
       if (!tile_live) {  // shadow tile of an odd tail: keep the TMEM handshake, store nothing
         const int as_ = tile_iter & 1;
         mbar_wait(&tmem_full[as_], (tile_iter >> 1) & 1);
@@ -284,7 +320,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // overlaps with tcgen05.ld instead of sitting in front of the first use.
         uint4 rres[8];
         const bool has_res = p.epi_mode == SEMSEG_EPI_AFFINE && p.residual != nullptr && row_valid;
-        if (has_res) {
+        if (has_res && !kSplit) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_pitch + c0);
 #pragma unroll
           for (int j8 = 0; j8 < 8; ++j8) rres[j8] = rp[j8];
@@ -298,14 +334,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
         if (p.epi_mode == SEMSEG_EPI_F32) {
           if (row_valid) {
-            float* orow = p.out_f32 + pix * p.out_pitch;
+            float* orow = p.out_f32 + k_slice * p.slice_stride + pix * p.out_pitch;
+            const bool bias = p.shift != nullptr && k_slice == 0;
+            if (c0 + 64 <= p.Cout && (p.out_pitch & 3) == 0) {   // whole chunk inside: 16-byte stores
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              const int c = c0 + j;
-              if (c < p.Cout) {
-                float a = __uint_as_float(v[j >> 5][j & 31]);
-                if (p.shift) a += __ldg(p.shift + c);
-                orow[c] = a;
+              for (int j4 = 0; j4 < 16; ++j4) {
+                float4 o;
+                o.x = __uint_as_float(v[j4 >> 3][(4 * j4 + 0) & 31]);
+                o.y = __uint_as_float(v[j4 >> 3][(4 * j4 + 1) & 31]);
+                o.z = __uint_as_float(v[j4 >> 3][(4 * j4 + 2) & 31]);
+                o.w = __uint_as_float(v[j4 >> 3][(4 * j4 + 3) & 31]);
+                if (bias) {
+                  o.x += __ldg(p.shift + c0 + 4 * j4);
+                  o.y += __ldg(p.shift + c0 + 4 * j4 + 1);
+                  o.z += __ldg(p.shift + c0 + 4 * j4 + 2);
+                  o.w += __ldg(p.shift + c0 + 4 * j4 + 3);
+                }
+                *reinterpret_cast<float4*>(orow + c0 + 4 * j4) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) {
+                const int c = c0 + j;
+                if (c < p.Cout) {
+                  float a = __uint_as_float(v[j >> 5][j & 31]);
+                  if (bias) a += __ldg(p.shift + c);
+                  orow[c] = a;
+                }
               }
             }
           }
@@ -317,13 +372,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j8 = 0; j8 < 8; ++j8) {
             float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (has_res) {
-              const uint4 rv = rres[j8];
-              const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+              if constexpr (kSplit) {   // hi + lo planes, loaded here (no prefetch: register budget)
+                const long long ro = pix * p.res_pitch + c0 + j8 * 8;
+                const uint4 rh = *reinterpret_cast<const uint4*>(p.residual + ro);
+                const uint4 rl = *reinterpret_cast<const uint4*>(p.residual_lo + ro);
+                const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&rh);
+                const __nv_bfloat162* pl = reinterpret_cast<const __nv_bfloat162*>(&rl);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = __bfloat1622float2(rp[q]);
-                r[2 * q] = f.x;
-                r[2 * q + 1] = f.y;
+                for (int q = 0; q < 4; ++q) {
+                  const float2 fh = __bfloat1622float2(ph[q]);
+                  const float2 fl = __bfloat1622float2(pl[q]);
+                  r[2 * q] = fh.x + fl.x;
+                  r[2 * q + 1] = fh.y + fl.y;
+                }
+              } else {
+                const uint4 rv = rres[j8];
+                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = __bfloat1622float2(rp[q]);
+                  r[2 * q] = f.x;
+                  r[2 * q + 1] = f.y;
+                }
               }
             }
 #pragma unroll
@@ -342,8 +412,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
         // registers -> bf16 -> 128B-swizzled staging tile (row = pixel, 64 channels = 128 bytes)
         // one group: two staging buffers used alternately; two groups: one buffer each
-        uint8_t* obuf = out_stage + (kEpiGroups == 1 ? store_buf : grp) * kStageOutBytes;
-        if (et == 0) tma_store_wait_read<(kEpiGroups == 1 ? 1 : 0)>();  // the store that last read this buffer has drained
+        // split storage: buffer 0 = hi plane tile, buffer 1 = lo plane tile
+        uint8_t* obuf = out_stage + (kSplit ? 0 : (kEpiGroups == 1 ? store_buf : grp)) * kStageOutBytes;
+        if (et == 0) tma_store_wait_read<((kEpiGroups == 1 && !kSplit) ? 1 : 0)>();  // the store(s) that last read the buffer(s) drained
         named_bar_sync(bar_id, kEpiGroupThreads);
 #pragma unroll
         for (int j8 = 0; j8 < 8; ++j8) {
@@ -354,6 +425,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           o.z = pack_bf16x2(__uint_as_float(v[b >> 5][(b + 4) & 31]), __uint_as_float(v[b >> 5][(b + 5) & 31]));
           o.w = pack_bf16x2(__uint_as_float(v[b >> 5][(b + 6) & 31]), __uint_as_float(v[b >> 5][(b + 7) & 31]));
           *reinterpret_cast<uint4*>(obuf + row * 128 + ((j8 ^ (row & 7)) << 4)) = o;
+          if constexpr (kSplit) {   // lo = value - float(hi), staged in the second buffer
+            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&o);
+            float l[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 hf = __bfloat1622float2(hp[q]);
+              l[2 * q] = __uint_as_float(v[b >> 5][(b + 2 * q) & 31]) - hf.x;
+              l[2 * q + 1] = __uint_as_float(v[b >> 5][(b + 2 * q + 1) & 31]) - hf.y;
+            }
+            uint4 ol;
+            ol.x = pack_bf16x2(l[0], l[1]);
+            ol.y = pack_bf16x2(l[2], l[3]);
+            ol.z = pack_bf16x2(l[4], l[5]);
+            ol.w = pack_bf16x2(l[6], l[7]);
+            *reinterpret_cast<uint4*>(obuf + kStageOutBytes + row * 128 + ((j8 ^ (row & 7)) << 4)) = ol;
+          }
         }
         fence_proxy_async_smem();
         if (do_stats) {
@@ -368,7 +455,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           auto add_row = [&](int rr, int sw) {  // sw = rr & 7 (the row's swizzle phase)
             const __nv_bfloat162 bv =
                 *reinterpret_cast<const __nv_bfloat162*>(base + rr * 128 + ((chunk16 ^ sw) << 4));
-            const float2 f = __bfloat1622float2(bv);
+            float2 f = __bfloat1622float2(bv);
+            if constexpr (kSplit) {
+              const float2 fl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
+                  base + kStageOutBytes + rr * 128 + ((chunk16 ^ sw) << 4)));
+              f.x += fl.x;
+              f.y += fl.y;
+            }
             s0 += f.x;
             s1 += f.y;
             q0 = fmaf(f.x, f.x, q0);
@@ -401,6 +494,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         named_bar_sync(bar_id, kEpiGroupThreads);
         if (et == 0) {
           tma_store_4d(&tmC, obuf, c0, w0, h0, img);
+          if (kSplit) tma_store_4d(&tmC_lo, obuf + kStageOutBytes, c0, w0, h0, img);
           tma_store_commit();
         }
         store_buf ^= 1;
@@ -456,21 +550,28 @@ static int epi_groups_wanted() {
   return v;
 }
 
-template <int BLOCK_N, int kEpiGroups>
-static int launch_conv_g(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvKParams& kp,
-                         bool clustered, int grid, cudaStream_t stream) {
+struct ConvMaps {
+  CUtensorMap a, b, c, a_lo, b_lo, c_lo;
+};
+
+template <int BLOCK_N, int kEpiGroups, bool kSplit>
+static int launch_conv_g(const ConvMaps& tm, const ConvKParams& kp, bool clustered, int grid, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, false, kEpiGroups>,
+  // the opt-in to > 48 KB of dynamic shared memory is per device: set it once for every device this process uses
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
+    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, false, kEpiGroups, kSplit>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, true, kEpiGroups>,
+    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, true, kEpiGroups, kSplit>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
   }
   constexpr int kThreads = conv_threads(kEpiGroups);
   if (!clustered) {
-    conv_igemm_kernel<BLOCK_N, false, kEpiGroups><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, kp);
+    conv_igemm_kernel<BLOCK_N, false, kEpiGroups, kSplit><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(
+        tm.a, tm.b, tm.c, tm.a_lo, tm.b_lo, tm.c_lo, kp);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -484,19 +585,21 @@ static int launch_conv_g(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, true, kEpiGroups>, tmA, tmB, tmC, kp));
+    SB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, true, kEpiGroups, kSplit>, tm.a, tm.b, tm.c, tm.a_lo,
+                               tm.b_lo, tm.c_lo, kp));
   }
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
 
 template <int BLOCK_N>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvKParams& kp,
-                       bool clustered, int grid, cudaStream_t stream) {
+static int launch_conv(const ConvMaps& tm, const ConvKParams& kp, bool split, bool clustered, int grid,
+                       cudaStream_t stream) {
+  if (split) return launch_conv_g<BLOCK_N, 1, true>(tm, kp, clustered, grid, stream);
   if constexpr (BLOCK_N >= 128) {
-    if (epi_groups_wanted() == 2) return launch_conv_g<BLOCK_N, 2>(tmA, tmB, tmC, kp, clustered, grid, stream);
+    if (epi_groups_wanted() == 2) return launch_conv_g<BLOCK_N, 2, false>(tm, kp, clustered, grid, stream);
   }
-  return launch_conv_g<BLOCK_N, 1>(tmA, tmB, tmC, kp, clustered, grid, stream);
+  return launch_conv_g<BLOCK_N, 1, false>(tm, kp, clustered, grid, stream);
 }
 
 }  // namespace sb
@@ -507,6 +610,14 @@ static int conv_block_n(int Cout) {
 }
 
 // Rows of the RAW-epilogue statistics buffer = number of CTAs the kernel will launch for this problem.
+// K blocks (64-channel block x tap) of a conv, and the slice count that keeps one accumulation chain <= max_kblocks.
+extern "C" int semseg_conv_k_slices(int Cin, int taps, int max_kblocks) {
+  if (Cin <= 0 || taps <= 0 || max_kblocks <= 0) return SEMSEG_E_INVALID;
+  const int total = taps * sb::cdiv(Cin, sb::kBlockK);
+  const int per = sb::cdiv(total, sb::cdiv(total, max_kblocks));
+  return sb::cdiv(total, per);
+}
+
 extern "C" int semseg_conv_stats_rows(int N, int H, int W, int Cout) {
   if (N <= 0 || H <= 0 || W <= 0 || Cout <= 0) return SEMSEG_E_INVALID;
   int bh, bw;
@@ -544,35 +655,67 @@ extern "C" int semseg_conv_fprop(const semseg_conv_desc* d, void* stream_) {
   kp.epi_mode = d->epi_mode; kp.relu = d->relu;
   kp.scale = d->scale; kp.shift = d->shift;
   kp.residual = static_cast<const __nv_bfloat16*>(d->residual); kp.res_pitch = d->res_pitch;
+  kp.residual_lo = static_cast<const __nv_bfloat16*>(d->residual_lo);
+  const bool split = d->x_lo != nullptr;   // bf16x3 operand mode: hi/lo planes for x, w, y, residual
+  kp.nseg = split ? 3 : 1;
+  if (split) {
+    SB_CHECK_ARG(d->w_split != 0, "conv: split activations need split weights (w_split)");
+    SB_CHECK_ARG(d->epi_mode == SEMSEG_EPI_F32 || d->y_lo != nullptr, "conv: split input needs a split output (y_lo)");
+    SB_CHECK_ARG(!d->residual || d->residual_lo, "conv: split input needs a split residual (residual_lo)");
+  } else {
+    SB_CHECK_ARG(!d->y_lo && !d->residual_lo, "conv: lo planes given without x_lo");
+  }
   kp.out_f32 = d->out_f32; kp.out_pitch = d->out_pitch;
   kp.stats_partial = d->stats_partial;
 
   const int block_n = conv_block_n(d->Cout);
   kp.n_tiles = cdiv(d->Cout, block_n);
+  kp.k_slices = 1;
+  kp.kb_per_slice = kp.taps * kp.k_chunks;
+  kp.slice_stride = 0;
+  if (d->k_slices > 1) {
+    SB_CHECK_ARG(d->epi_mode == SEMSEG_EPI_F32, "conv: K slicing needs the F32 epilogue (partials are fp32)");
+    SB_CHECK_ARG(d->slice_stride >= static_cast<long long>(d->N) * d->H * d->W * d->out_pitch,
+                 "conv: slice_stride too small for an [N,H,W,out_pitch] partial");
+    kp.kb_per_slice = cdiv(kp.taps * kp.k_chunks, d->k_slices);
+    kp.k_slices = cdiv(kp.taps * kp.k_chunks, kp.kb_per_slice);   // no empty slices
+    SB_CHECK_ARG(kp.k_slices == d->k_slices, "conv: k_slices %d not realisable for %d K blocks (use %d)", d->k_slices,
+                 kp.taps * kp.k_chunks, kp.k_slices);
+    kp.slice_stride = d->slice_stride;
+  }
   bool clustered = false;
-  const int grid = conv_grid(kp.num_m_tiles, kp.n_tiles, &clustered);
+  const int grid = conv_grid(kp.num_m_tiles, kp.n_tiles * kp.k_slices, &clustered);
 
   // A: input activations [Nin][Hin][Win][x_pitch] viewed as (C, W, H, N)
-  CUtensorMap tmA, tmB, tmC;
+  ConvMaps tm;
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->Nin};
     uint64_t str[3] = {(uint64_t)d->x_pitch * 2, (uint64_t)d->x_pitch * 2 * d->Win,
                        (uint64_t)d->x_pitch * 2 * d->Win * d->Hin};
     uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)kp.bw, (uint32_t)kp.bh, 1};
-    int r = encode_tmap_bf16(&tmA, d->x, 4, dims, str, box);
+    int r = encode_tmap_bf16(&tm.a, d->x, 4, dims, str, box);
     if (r) return r;
+    tm.a_lo = tm.a;
+    if (split && (r = encode_tmap_bf16(&tm.a_lo, d->x_lo, 4, dims, str, box))) return r;
   }
   {
     uint64_t dims[3] = {(uint64_t)d->w_cols, (uint64_t)d->w_rows, (uint64_t)d->n_wtaps};
     uint64_t str[2] = {(uint64_t)d->w_cols * 2, (uint64_t)d->w_cols * 2 * d->w_rows};
     // clustered: each CTA loads (and multicasts) half of the weight rows of the tile
     uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)(clustered ? block_n / 2 : block_n), 1};
-    int r = encode_tmap_bf16(&tmB, d->w, 3, dims, str, box);
+    int r = encode_tmap_bf16(&tm.b, d->w, 3, dims, str, box);
     if (r) return r;
+    tm.b_lo = tm.b;
+    if (split) {   // the lo slab follows the hi slab (semseg_pack_weights with split != 0)
+      const __nv_bfloat16* w_lo =
+          static_cast<const __nv_bfloat16*>(d->w) + static_cast<size_t>(d->n_wtaps) * d->w_rows * d->w_cols;
+      if ((r = encode_tmap_bf16(&tm.b_lo, w_lo, 3, dims, str, box))) return r;
+    }
   }
   if (d->epi_mode == SEMSEG_EPI_F32) {
     SB_CHECK_ARG(d->out_f32 != nullptr && d->out_pitch >= d->Cout, "conv: F32 epilogue needs out_f32/out_pitch");
-    tmC = tmA;  // unused
+    tm.c = tm.a;  // unused
+    tm.c_lo = tm.a;
   } else {
     SB_CHECK_ARG(d->y != nullptr, "conv: null y");
     SB_CHECK_ARG(d->Cout % 64 == 0, "conv: bf16 epilogue needs Cout %% 64 == 0 (got %d)", d->Cout);
@@ -582,12 +725,14 @@ extern "C" int semseg_conv_fprop(const semseg_conv_desc* d, void* stream_) {
     uint64_t str[3] = {(uint64_t)d->y_pitch * 2, (uint64_t)d->y_pitch * 2 * d->W,
                        (uint64_t)d->y_pitch * 2 * d->W * d->H};
     uint32_t box[4] = {64u, (uint32_t)kp.bw, (uint32_t)kp.bh, 1};
-    int r = encode_tmap_bf16(&tmC, d->y, 4, dims, str, box);
+    int r = encode_tmap_bf16(&tm.c, d->y, 4, dims, str, box);
     if (r) return r;
+    tm.c_lo = tm.c;
+    if (split && (r = encode_tmap_bf16(&tm.c_lo, d->y_lo, 4, dims, str, box))) return r;
   }
   switch (block_n) {
-    case 256: return launch_conv<256>(tmA, tmB, tmC, kp, clustered, grid, stream);
-    case 128: return launch_conv<128>(tmA, tmB, tmC, kp, clustered, grid, stream);
-    default: return launch_conv<64>(tmA, tmB, tmC, kp, clustered, grid, stream);
+    case 256: return launch_conv<256>(tm, kp, split, clustered, grid, stream);
+    case 128: return launch_conv<128>(tm, kp, split, clustered, grid, stream);
+    default: return launch_conv<64>(tm, kp, split, clustered, grid, stream);
   }
 }

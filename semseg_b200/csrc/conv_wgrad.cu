@@ -46,6 +46,7 @@ struct WgradKParams {
   int tu, cin_boxes, unit_taps, oob_img;
   int dh[SEMSEG_MAX_TAPS], dw[SEMSEG_MAX_TAPS], img_add[SEMSEG_MAX_TAPS];
   int img_mul;
+  int nseg;    // 1 = bf16 operands; 3 = bf16x3 (dy_hi*x_hi, dy_lo*x_hi, dy_hi*x_lo accumulated in TMEM)
   float* out;  // [n_splits][taps][Cout][Cin]
 };
 
@@ -54,6 +55,7 @@ struct WgradKParams {
 template <int kWgBlockN, bool kPair>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ CUtensorMap tmDY_lo, const __grid_constant__ CUtensorMap tmX_lo,
                   const WgradKParams p) {
   constexpr int kWgBBoxes = kPair ? WgCfg<kWgBlockN>::kPairBBoxes : WgCfg<kWgBlockN>::kBBoxes;
   constexpr int kWgStageBytes = kPair ? WgCfg<kWgBlockN>::kPairStageBytes : WgCfg<kWgBlockN>::kStageBytes;
@@ -93,6 +95,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDY);
     tma_prefetch_desc(&tmX);
+    if (p.nseg > 1) {
+      tma_prefetch_desc(&tmDY_lo);
+      tma_prefetch_desc(&tmX_lo);
+    }
     for (int i = 0; i < kWgStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -133,7 +139,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         const int b0 = split * p.boxes_per_split;
         const int b1 = min(b0 + p.boxes_per_split, p.num_boxes);
         const int tiles_per_img = p.tiles_h * p.tiles_w;
-        for (int b = b0; b < b1; ++b, ++it) {
+        for (int bs = b0 * p.nseg; bs < b1 * p.nseg; ++bs, ++it) {
+          const int b = bs / p.nseg;
+          const int seg = bs - b * p.nseg;   // split storage: every pixel box is issued as three operand segments
+          const CUtensorMap* mDY = seg == 1 ? &tmDY_lo : &tmDY;
+          const CUtensorMap* mX = seg == 2 ? &tmX_lo : &tmX;
           const int s = it % kWgStages;
           const uint32_t par = (it / kWgStages) & 1;
           mbar_wait(&empty_bar[s], par ^ 1);
@@ -147,30 +157,30 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             if (is_leader) mbar_expect_tx(&full_bar[s], stage_tx);
 #pragma unroll
             for (int i = 0; i < kWgABoxes; ++i)
-              tma_load_4d_2sm(st + i * kWgBoxBytes, &tmDY, lead_bar, co_t * 128 + i * 64, w0, h0, img);
+              tma_load_4d_2sm(st + i * kWgBoxBytes, mDY, lead_bar, co_t * 128 + i * 64, w0, h0, img);
 #pragma unroll
             for (int i = 0; i < kWgBBoxes; ++i)
-              tma_load_4d_2sm(st + (kWgABoxes + i) * kWgBoxBytes, &tmX, lead_bar,
+              tma_load_4d_2sm(st + (kWgABoxes + i) * kWgBoxBytes, mX, lead_bar,
                               ci_t * kWgBlockN + static_cast<int>(cta_rank) * (kWgBlockN / 2) + i * 64,
                               w0 + p.dw[tap], h0 + p.dh[tap], img * p.img_mul + p.img_add[tap]);
           } else {
             mbar_expect_tx(&full_bar[s], stage_tx);
 #pragma unroll
             for (int i = 0; i < kWgABoxes; ++i)
-              tma_load_4d(st + i * kWgBoxBytes, &tmDY, &full_bar[s], co_t * 128 + i * 64, w0, h0, img);
+              tma_load_4d(st + i * kWgBoxBytes, mDY, &full_bar[s], co_t * 128 + i * 64, w0, h0, img);
             if (p.tu > 1) {
 #pragma unroll
               for (int i = 0; i < kWgBBoxes; ++i) {   // box i = (tap of the group, 64-channel block)
                 const int ti = tap * p.tu + i / p.cin_boxes;
                 const bool live = ti < p.taps;        // dead taps of the last group: fully out-of-range box -> zeros
                 const int tt = live ? ti : 0;
-                tma_load_4d(st + (kWgABoxes + i) * kWgBoxBytes, &tmX, &full_bar[s], (i % p.cin_boxes) * 64,
+                tma_load_4d(st + (kWgABoxes + i) * kWgBoxBytes, mX, &full_bar[s], (i % p.cin_boxes) * 64,
                             w0 + p.dw[tt], h0 + p.dh[tt], live ? img * p.img_mul + p.img_add[tt] : p.oob_img);
               }
             } else {
 #pragma unroll
               for (int i = 0; i < kWgBBoxes; ++i)
-                tma_load_4d(st + (kWgABoxes + i) * kWgBoxBytes, &tmX, &full_bar[s], ci_t * kWgBlockN + i * 64,
+                tma_load_4d(st + (kWgABoxes + i) * kWgBoxBytes, mX, &full_bar[s], ci_t * kWgBlockN + i * 64,
                             w0 + p.dw[tap], h0 + p.dh[tap], img * p.img_mul + p.img_add[tap]);
             }
           }
@@ -192,7 +202,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         mbar_wait(&tmem_empty[as], apar ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kWgBlockN);
-        for (int b = b0; b < b1; ++b, ++it) {
+        for (int b = b0 * p.nseg; b < b1 * p.nseg; ++b, ++it) {
           const int s = it % kWgStages;
           const uint32_t par = (it / kWgStages) & 1;
           mbar_wait(&full_bar[s], par);
@@ -207,10 +217,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             // 16 pixels along K = 2048 bytes -> +128 in 16-byte units
             if (kPair)
               umma_bf16_2sm(d_tmem, adesc + static_cast<uint64_t>(k * 128), bdesc + static_cast<uint64_t>(k * 128),
-                            idesc, (b > b0 || k > 0) ? 1u : 0u);
+                            idesc, (b > b0 * p.nseg || k > 0) ? 1u : 0u);
             else
               umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 128), bdesc + static_cast<uint64_t>(k * 128), idesc,
-                        (b > b0 || k > 0) ? 1u : 0u);
+                        (b > b0 * p.nseg || k > 0) ? 1u : 0u);
           }
           if (kPair) umma_commit_2sm_mcast(&empty_bar[s], static_cast<uint16_t>(3));
           else umma_commit(&empty_bar[s]);
@@ -362,16 +372,19 @@ static bool wgrad_pair_enabled() {
 }
 
 template <int BN, bool kPair>
-static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradKParams& kp, int grid,
-                        cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensorMap& tmDY_lo,
+                        const CUtensorMap& tmX_lo, const WgradKParams& kp, int grid, cudaStream_t stream) {
+  // per-device opt-in to > 48 KB dynamic shared memory (see conv_igemm.cu)
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
     SB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  WgCfg<BN>::kSmemBytes));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
   }
   if (!kPair) {
-    conv_wgrad_kernel<BN, false><<<grid, kWgThreads, WgCfg<BN>::kSmemBytes, stream>>>(tmDY, tmX, kp);
+    conv_wgrad_kernel<BN, false><<<grid, kWgThreads, WgCfg<BN>::kSmemBytes, stream>>>(tmDY, tmX, tmDY_lo, tmX_lo, kp);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -385,7 +398,7 @@ static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const W
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SB_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN, true>, tmDY, tmX, kp));
+    SB_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN, true>, tmDY, tmX, tmDY_lo, tmX_lo, kp));
   }
   return SEMSEG_OK;
 }
@@ -422,6 +435,13 @@ static void wgrad_geometry(const semseg_wgrad_desc* d, WgradKParams* kp) {
     if (splits > max_by_k) splits = max_by_k;
     if (splits > 64) splits = 64;
     if (splits < 1) splits = 1;
+    if (d->x_lo != nullptr) {
+      // bf16x3: bound one accumulation chain to 21 pixel boxes (21 x 4 MMA steps x 3 segments = 252 steps): the tensor
+      // core's fp32 accumulation truncates (~2^-24 per step towards zero, tools/probe_accum.py); the fixed-order fp32
+      // reduction of the split partials rounds to nearest.
+      const int need = cdiv(kp->num_boxes, 21);
+      if (splits < need) splits = need;
+    }
   }
   kp->boxes_per_split = cdiv(kp->num_boxes, splits);
   kp->n_splits = cdiv(kp->num_boxes, kp->boxes_per_split);  // no empty splits
@@ -455,8 +475,11 @@ extern "C" int semseg_conv_wgrad(const semseg_wgrad_desc* d, void* stream_) {
   }
   kp.img_mul = d->img_mul;
   kp.out = d->dw_partial;
+  const bool split = d->x_lo != nullptr;
+  SB_CHECK_ARG((d->dy_lo != nullptr) == split, "wgrad: x and dy must use the same storage form (plain or split)");
+  kp.nseg = split ? 3 : 1;
 
-  CUtensorMap tmDY, tmX;
+  CUtensorMap tmDY, tmX, tmDY_lo, tmX_lo;
   {
     uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t str[3] = {(uint64_t)d->dy_pitch * 2, (uint64_t)d->dy_pitch * 2 * d->W,
@@ -464,6 +487,8 @@ extern "C" int semseg_conv_wgrad(const semseg_wgrad_desc* d, void* stream_) {
     uint32_t box[4] = {64u, (uint32_t)kp.bw, (uint32_t)kp.bh, 1};
     int r = encode_tmap_bf16(&tmDY, d->dy, 4, dims, str, box);
     if (r) return r;
+    tmDY_lo = tmDY;
+    if (split && (r = encode_tmap_bf16(&tmDY_lo, d->dy_lo, 4, dims, str, box))) return r;
   }
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->Nin};
@@ -472,20 +497,22 @@ extern "C" int semseg_conv_wgrad(const semseg_wgrad_desc* d, void* stream_) {
     uint32_t box[4] = {64u, (uint32_t)kp.bw, (uint32_t)kp.bh, 1};
     int r = encode_tmap_bf16(&tmX, d->x, 4, dims, str, box);
     if (r) return r;
+    tmX_lo = tmX;
+    if (split && (r = encode_tmap_bf16(&tmX_lo, d->x_lo, 4, dims, str, box))) return r;
   }
   const int units = kp.unit_taps * kp.co_tiles * kp.ci_tiles * kp.n_splits;
   int rc = SEMSEG_OK;
   if (kp.pair) {
     const int max_clusters = num_sms() / 2;
     const int grid = 2 * (units < max_clusters ? units : max_clusters);
-    rc = kp.block_n == 256 ? launch_wgrad<256, true>(tmDY, tmX, kp, grid, stream)
-                           : launch_wgrad<128, true>(tmDY, tmX, kp, grid, stream);
+    rc = kp.block_n == 256 ? launch_wgrad<256, true>(tmDY, tmX, tmDY_lo, tmX_lo, kp, grid, stream)
+                           : launch_wgrad<128, true>(tmDY, tmX, tmDY_lo, tmX_lo, kp, grid, stream);
   } else {
     const int grid = units < num_sms() ? units : num_sms();
     switch (kp.block_n) {
-      case 256: rc = launch_wgrad<256, false>(tmDY, tmX, kp, grid, stream); break;
-      case 128: rc = launch_wgrad<128, false>(tmDY, tmX, kp, grid, stream); break;
-      default: rc = launch_wgrad<64, false>(tmDY, tmX, kp, grid, stream); break;
+      case 256: rc = launch_wgrad<256, false>(tmDY, tmX, tmDY_lo, tmX_lo, kp, grid, stream); break;
+      case 128: rc = launch_wgrad<128, false>(tmDY, tmX, tmDY_lo, tmX_lo, kp, grid, stream); break;
+      default: rc = launch_wgrad<64, false>(tmDY, tmX, tmDY_lo, tmX_lo, kp, grid, stream); break;
     }
   }
   if (rc) return rc;

@@ -3,12 +3,14 @@
 //   - fp32 OIHW master weights -> bf16 [tap][row][col] operand slabs for the implicit-GEMM kernels
 #include "host_common.h"
 #include "ptx.cuh"
+#include "act.cuh"
 
 namespace sb {
 
 // 32x32 tiled transpose between [C][HW] (NCHW plane) and [HW][pitch] (NHWC) per image.
 template <typename TIn, typename TOut>
-__global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int C, int HW, int out_pitch) {
+__global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, TOut* __restrict__ out_lo, int C,
+                                    int HW, int out_pitch) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -21,12 +23,20 @@ __global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ in, TOut* __restrict
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int p = p0 + r, c = c0 + threadIdx.x;
-    if (p < HW && c < C) dst[static_cast<size_t>(p) * out_pitch + c] = static_cast<TOut>(tile[threadIdx.x][r]);
+    if (p < HW && c < C) {
+      const float v = tile[threadIdx.x][r];
+      const TOut hi = static_cast<TOut>(v);
+      dst[static_cast<size_t>(p) * out_pitch + c] = hi;
+      if (out_lo)   // split storage: lo = v - hi
+        out_lo[static_cast<size_t>(n) * HW * out_pitch + static_cast<size_t>(p) * out_pitch + c] =
+            static_cast<TOut>(v - static_cast<float>(hi));
+    }
   }
 }
 
 template <typename TIn, typename TOut>
-__global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int C, int HW, int in_pitch) {
+__global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ in, const TIn* __restrict__ in_lo, TOut* __restrict__ out,
+                                    int C, int HW, int in_pitch) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -34,7 +44,12 @@ __global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ in, TOut* __restrict
   TOut* dst = out + static_cast<size_t>(n) * C * HW;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int p = p0 + r, c = c0 + threadIdx.x;
-    tile[r][threadIdx.x] = (p < HW && c < C) ? static_cast<float>(src[static_cast<size_t>(p) * in_pitch + c]) : 0.f;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      v = static_cast<float>(src[static_cast<size_t>(p) * in_pitch + c]);
+      if (in_lo) v += static_cast<float>(in_lo[static_cast<size_t>(n) * HW * in_pitch + static_cast<size_t>(p) * in_pitch + c]);
+    }
+    tile[r][threadIdx.x] = v;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -44,8 +59,9 @@ __global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ in, TOut* __restrict
 }
 
 // w[co][ci][t] fp32 -> wf[t][co][ci] bf16 (rows_f x cols_f, zero padded). One thread per output element.
+// split != 0: the lo slab (bf16(v - hi)) is written directly behind the hi slab.
 __global__ void pack_wf_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, __nv_bfloat16* __restrict__ wf,
-                               int rows, int cols) {
+                               int rows, int cols, int split) {
   const size_t total = static_cast<size_t>(taps) * rows * cols;
   for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -55,13 +71,15 @@ __global__ void pack_wf_kernel(const float* __restrict__ w, int Cout, int Cin, i
     const int t = static_cast<int>(r / rows);
     float v = 0.f;
     if (co < Cout && ci < Cin) v = w[(static_cast<size_t>(co) * Cin + ci) * taps + t];
-    wf[idx] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    wf[idx] = hi;
+    if (split) wf[total + idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
 }
 
 // w[co][ci][t] fp32 -> wd[t][ci][co] bf16 via a 32x32 smem transpose of the (co, ci) plane per tap.
 __global__ void pack_wd_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, __nv_bfloat16* __restrict__ wd,
-                               int rows, int cols) {
+                               int rows, int cols, int split) {
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -72,8 +90,13 @@ __global__ void pack_wd_kernel(const float* __restrict__ w, int Cout, int Cin, i
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int ci = ci0 + r, co = co0 + threadIdx.x;
-    if (ci < rows && co < cols)
-      wd[(static_cast<size_t>(t) * rows + ci) * cols + co] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+    if (ci < rows && co < cols) {
+      const float v = tile[threadIdx.x][r];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const size_t o = (static_cast<size_t>(t) * rows + ci) * cols + co;
+      wd[o] = hi;
+      if (split) wd[static_cast<size_t>(gridDim.z) * rows * cols + o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
   }
 }
 
@@ -111,18 +134,26 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const semseg_pack_item*
     __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(it.wf);
     for (int idx = threadIdx.x; idx < total; idx += 256) {
       const int ci_l = idx & 31, co_l = (idx >> 5) & 31, t = idx >> 10;
-      if (co_l < nco && ci0 + ci_l < it.cols_f)
-        wf[(static_cast<size_t>(t) * it.Cout + co0 + co_l) * it.cols_f + ci0 + ci_l] =
-            __float2bfloat16_rn(pk_tile[co_l * pitch + ci_l * taps + t]);
+      if (co_l < nco && ci0 + ci_l < it.cols_f) {
+        const float v = pk_tile[co_l * pitch + ci_l * taps + t];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const size_t o = (static_cast<size_t>(t) * it.Cout + co0 + co_l) * it.cols_f + ci0 + ci_l;
+        wf[o] = hi;
+        if (it.split) wf[static_cast<size_t>(taps) * it.Cout * it.cols_f + o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      }
     }
   }
   if (it.wd) {
     __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(it.wd);
     for (int idx = threadIdx.x; idx < total; idx += 256) {
       const int co_l = idx & 31, ci_l = (idx >> 5) & 31, t = idx >> 10;
-      if (ci_l < nci && co0 + co_l < it.cols_d)
-        wd[(static_cast<size_t>(t) * it.Cin + ci0 + ci_l) * it.cols_d + co0 + co_l] =
-            __float2bfloat16_rn(pk_tile[co_l * pitch + ci_l * taps + t]);
+      if (ci_l < nci && co0 + co_l < it.cols_d) {
+        const float v = pk_tile[co_l * pitch + ci_l * taps + t];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const size_t o = (static_cast<size_t>(t) * it.Cin + ci0 + ci_l) * it.cols_d + co0 + co_l;
+        wd[o] = hi;
+        if (it.split) wd[static_cast<size_t>(taps) * it.Cin * it.cols_d + o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      }
     }
   }
 }
@@ -240,7 +271,7 @@ extern "C" int semseg_phases_to_space(const void* xp, int N, int H, int W, int C
 }
 
 extern "C" int semseg_pack_weights(const float* w_oihw, int Cout, int Cin, int taps, void* wf, int rows_f, int cols_f,
-                                   void* wd, int rows_d, int cols_d, void* stream_) {
+                                   void* wd, int rows_d, int cols_d, int split, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(w_oihw && Cout > 0 && Cin > 0 && taps > 0 && taps <= SEMSEG_MAX_TAPS, "pack_weights: bad args");
   if (wf) {
@@ -250,14 +281,15 @@ extern "C" int semseg_pack_weights(const float* w_oihw, int Cout, int Cin, int t
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     pack_wf_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(w_oihw, Cout, Cin, taps, static_cast<bf16*>(wf),
-                                                                     rows_f, cols_f);
+                                                                     rows_f, cols_f, split);
     SB_LAUNCHED();
   }
   if (wd) {
     SB_CHECK_ARG(rows_d >= Cin && cols_d >= Cout && cols_d % 8 == 0, "pack_weights: bad wd dims %d x %d", rows_d,
                  cols_d);
     dim3 grid(cdiv(rows_d, 32), cdiv(cols_d, 32), taps);
-    pack_wd_kernel<<<grid, dim3(32, 8), 0, stream>>>(w_oihw, Cout, Cin, taps, static_cast<bf16*>(wd), rows_d, cols_d);
+    pack_wd_kernel<<<grid, dim3(32, 8), 0, stream>>>(w_oihw, Cout, Cin, taps, static_cast<bf16*>(wd), rows_d, cols_d,
+                                                     split);
     SB_LAUNCHED();
   }
   return SEMSEG_OK;
@@ -289,23 +321,24 @@ extern "C" int semseg_pack_weights_multi(const semseg_pack_item* items_dev, int 
   return SEMSEG_OK;
 }
 
-extern "C" int semseg_nchw_f32_to_nhwc_bf16(const float* in, void* out, int N, int C, int H, int W, int out_pitch,
-                                            void* stream_) {
+extern "C" int semseg_nchw_f32_to_nhwc_bf16(const float* in, void* out, void* out_lo, int N, int C, int H, int W,
+                                            int out_pitch, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && out_pitch >= C, "nchw_f32_to_nhwc_bf16: bad args");
   dim3 grid(cdiv(H * W, 32), cdiv(C, 32), N);
-  nchw_to_nhwc_kernel<float, bf16><<<grid, dim3(32, 8), 0, stream>>>(in, static_cast<bf16*>(out), C, H * W, out_pitch);
+  nchw_to_nhwc_kernel<float, bf16><<<grid, dim3(32, 8), 0, stream>>>(in, static_cast<bf16*>(out),
+                                                                     static_cast<bf16*>(out_lo), C, H * W, out_pitch);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
 
-extern "C" int semseg_nhwc_bf16_to_nchw_f32(const void* in, float* out, int N, int C, int H, int W, int in_pitch,
-                                            void* stream_) {
+extern "C" int semseg_nhwc_bf16_to_nchw_f32(const void* in, const void* in_lo, float* out, int N, int C, int H, int W,
+                                            int in_pitch, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && in_pitch >= C, "nhwc_bf16_to_nchw_f32: bad args");
   dim3 grid(cdiv(H * W, 32), cdiv(C, 32), N);
-  nhwc_to_nchw_kernel<bf16, float><<<grid, dim3(32, 8), 0, stream>>>(static_cast<const bf16*>(in), out, C, H * W,
-                                                                    in_pitch);
+  nhwc_to_nchw_kernel<bf16, float><<<grid, dim3(32, 8), 0, stream>>>(
+      static_cast<const bf16*>(in), static_cast<const bf16*>(in_lo), out, C, H * W, in_pitch);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
@@ -315,7 +348,7 @@ extern "C" int semseg_nhwc_f32_to_nchw_f32(const float* in, float* out, int N, i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && in_pitch >= C, "nhwc_f32_to_nchw_f32: bad args");
   dim3 grid(cdiv(H * W, 32), cdiv(C, 32), N);
-  nhwc_to_nchw_kernel<float, float><<<grid, dim3(32, 8), 0, stream>>>(in, out, C, H * W, in_pitch);
+  nhwc_to_nchw_kernel<float, float><<<grid, dim3(32, 8), 0, stream>>>(in, nullptr, out, C, H * W, in_pitch);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }

@@ -5,29 +5,13 @@
 // dy of those whose recorded arg-max is this pixel. No atomics, every dx element written once.
 #include "host_common.h"
 #include "ptx.cuh"
+#include "act.cuh"
 
 namespace sb {
 
-__device__ __forceinline__ void mp_ld8(const __nv_bfloat16* p, float (&f)[8]) {
-  const uint4 v = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float2 t = __bfloat1622float2(h[q]);
-    f[2 * q] = t.x;
-    f[2 * q + 1] = t.y;
-  }
-}
-__device__ __forceinline__ void mp_st8(__nv_bfloat16* p, const float (&f)[8]) {
-  uint4 o;
-  o.x = pack_bf16x2(f[0], f[1]);
-  o.y = pack_bf16x2(f[2], f[3]);
-  o.z = pack_bf16x2(f[4], f[5]);
-  o.w = pack_bf16x2(f[6], f[7]);
-  *reinterpret_cast<uint4*>(p) = o;
-}
-
-__global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+template <bool S>
+__global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo,
+                                        __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y_lo,
                                         unsigned char* __restrict__ argcode, int N, int H, int W, int C, int Ho,
                                         int Wo) {
   const int groups = C >> 3;
@@ -54,7 +38,7 @@ __global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __n
         const int w = 2 * wo - 1 + kw;
         if (w < 0 || w >= W) continue;
         float f[8];
-        mp_ld8(x + ((static_cast<size_t>(n) * H + h) * W + w) * C + c0, f);
+        act_ld8<S>(x, x_lo, ((static_cast<long long>(n) * H + h) * W + w) * C + c0, f);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (f[q] > m[q] || code[q] == 255u) {  // first maximum in row-major window order (ATen's tie rule)
@@ -64,8 +48,8 @@ __global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __n
         }
       }
     }
-    const size_t o = ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c0;
-    mp_st8(y + o, m);
+    const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C + c0;
+    act_st8<S>(y, y_lo, o, m);
     if (argcode) {
       uint2 pk;
       pk.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
@@ -75,8 +59,10 @@ __global__ void maxpool3x3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __n
   }
 }
 
+template <bool S>
 __global__ void maxpool3x3s2_bwd_kernel(const unsigned char* __restrict__ argcode, const __nv_bfloat16* __restrict__ dy,
-                                        __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
+                                        const __nv_bfloat16* __restrict__ dy_lo, __nv_bfloat16* __restrict__ dx,
+                                        __nv_bfloat16* __restrict__ dx_lo, int N, int H, int W, int C, int Ho, int Wo) {
   const int groups = C >> 3;
   const long long total = static_cast<long long>(N) * H * W * groups;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -94,10 +80,10 @@ __global__ void maxpool3x3s2_bwd_kernel(const unsigned char* __restrict__ argcod
     for (int ho = ho_lo; ho <= ho_hi; ++ho) {
       for (int wo = wo_lo; wo <= wo_hi; ++wo) {
         const unsigned me = static_cast<unsigned>((h - (2 * ho - 1)) * 3 + (w - (2 * wo - 1)));  // my code in this window
-        const size_t o = ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c0;
+        const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C + c0;
         const uint2 pk = *reinterpret_cast<const uint2*>(argcode + o);
         float g[8];
-        mp_ld8(dy + o, g);
+        act_ld8<S>(dy, dy_lo, o, g);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const unsigned cq = ((q < 4 ? pk.x : pk.y) >> ((q & 3) * 8)) & 0xffu;
@@ -105,7 +91,7 @@ __global__ void maxpool3x3s2_bwd_kernel(const unsigned char* __restrict__ argcod
         }
       }
     }
-    mp_st8(dx + ((static_cast<size_t>(n) * H + h) * W + w) * C + c0, acc);
+    act_st8<S>(dx, dx_lo, ((static_cast<long long>(n) * H + h) * W + w) * C + c0, acc);
   }
 }
 
@@ -119,29 +105,34 @@ static int mp_blocks(long long total) {
 
 using namespace sb;
 
-extern "C" int semseg_maxpool3x3s2_fwd(const void* x, void* y, void* argcode, int N, int H, int W, int C,
-                                       void* stream_) {
+extern "C" int semseg_maxpool3x3s2_fwd(const void* x, const void* x_lo, void* y, void* y_lo, void* argcode, int N,
+                                       int H, int W, int C, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool_fwd: bad args");
+  SB_CHECK_ARG((x_lo != nullptr) == (y_lo != nullptr), "maxpool_fwd: input and output must use the same storage form");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
-  maxpool3x3s2_fwd_kernel<<<mp_blocks(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
-                                                               static_cast<__nv_bfloat16*>(y),
-                                                               static_cast<unsigned char*>(argcode), N, H, W, C, Ho,
-                                                               Wo);
+  typedef __nv_bfloat16 bf16;
+  SB_ACT_DISPATCH(x_lo != nullptr, maxpool3x3s2_fwd_kernel<kS><<<mp_blocks(total), 256, 0, stream>>>(
+                                       static_cast<const bf16*>(x), static_cast<const bf16*>(x_lo),
+                                       static_cast<bf16*>(y), static_cast<bf16*>(y_lo),
+                                       static_cast<unsigned char*>(argcode), N, H, W, C, Ho, Wo));
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
 
-extern "C" int semseg_maxpool3x3s2_bwd(const void* argcode, const void* dy, void* dx, int N, int H, int W, int C,
-                                       void* stream_) {
+extern "C" int semseg_maxpool3x3s2_bwd(const void* argcode, const void* dy, const void* dy_lo, void* dx, void* dx_lo,
+                                       int N, int H, int W, int C, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(argcode && dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "maxpool_bwd: bad args");
+  SB_CHECK_ARG((dy_lo != nullptr) == (dx_lo != nullptr), "maxpool_bwd: dy and dx must use the same storage form");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(N) * H * W * (C / 8);
-  maxpool3x3s2_bwd_kernel<<<mp_blocks(total), 256, 0, stream>>>(static_cast<const unsigned char*>(argcode),
-                                                               static_cast<const __nv_bfloat16*>(dy),
-                                                               static_cast<__nv_bfloat16*>(dx), N, H, W, C, Ho, Wo);
+  typedef __nv_bfloat16 bf16;
+  SB_ACT_DISPATCH(dy_lo != nullptr, maxpool3x3s2_bwd_kernel<kS><<<mp_blocks(total), 256, 0, stream>>>(
+                                        static_cast<const unsigned char*>(argcode), static_cast<const bf16*>(dy),
+                                        static_cast<const bf16*>(dy_lo), static_cast<bf16*>(dx),
+                                        static_cast<bf16*>(dx_lo), N, H, W, C, Ho, Wo));
   SB_LAUNCHED();
   return SEMSEG_OK;
 }

@@ -17,35 +17,51 @@ import torch.nn.functional as F
 
 from . import ops
 from . import p2p
+from . import precision
 from .dist_utils import gather_rank_stats
 from .ops import EPI_RAW, EPI_AFFINE, EPI_F32
 
 
 # ------------------------------------------------------------------------------------------------ helpers
-def packed(conv, need_dgrad=True):
-    """bf16 operand slabs of conv.weight, re-packed only when the parameter changed (optimizer step / load)."""
+def packed(conv, need_dgrad=True, split=False):
+    """bf16 operand slabs of conv.weight (hi + lo slabs when split), re-packed only when the parameter changed
+    (optimizer step / load). The cache key is (parameter version, storage pointer): in-place edits through `.data`
+    do not bump the version — call `invalidate_packs(model)` after such an edit."""
     w = conv.weight
-    key = (w._version, w.data_ptr(), need_dgrad)
+    key = (w._version, w.data_ptr(), need_dgrad, split)
     cache = conv.__dict__.get("_sb_pack")
     if cache is not None and cache[0] == key:
         return cache[1]
-    pw = ops.pack_weights(w, need_dgrad=need_dgrad)
+    if cache is not None and cache[0][:2] == key[:2] and cache[0][3] == split and cache[0][2]:
+        return cache[1]                       # a pack with dgrad slabs also serves a forward-only request
+    pw = ops.pack_weights(w, need_dgrad=need_dgrad, split=split)
     conv.__dict__["_sb_pack"] = (key, pw)
     return pw
 
 
-def packed_patches(conv):
+def invalidate_packs(model):
+    """Forget every cached operand slab of `model` (needed after weights were modified through `.data`, which does not
+    bump the version counter the cache is keyed on)."""
+    for m in model.modules():
+        m.__dict__.pop("_sb_pack", None)
+        m.__dict__.pop("_sb_pack_patches", None)
+    model.__dict__.pop("_sb_pack_plan", None)
+
+
+def packed_patches(conv, split=False):
     """Operand slab of the stem conv in its patch form (ops.im2col3x3s2): wf [1][Cout][32] with column
-    (r*3+s)*Cin + c = weight[:, c, r, s], zero padded; re-made only when the parameter changed."""
+    (r*3+s)*Cin + c = weight[:, c, r, s], zero padded ([2][1][Cout][32] = hi, lo slabs when split); re-made only when the
+    parameter changed."""
     w = conv.weight
-    key = (w._version, w.data_ptr(), "patches")
+    key = (w._version, w.data_ptr(), "patches", split)
     cache = conv.__dict__.get("_sb_pack_patches")
     if cache is not None and cache[0] == key:
         return cache[1]
     cout, cin = w.shape[0], w.shape[1]
-    flat = w.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin)
-    wf = torch.zeros((1, cout, 32), dtype=torch.bfloat16, device=w.device)
-    wf[0, :, :9 * cin] = flat
+    flat = torch.zeros((1, cout, 32), dtype=torch.float32, device=w.device)
+    flat[0, :, :9 * cin] = w.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    hi = flat.to(torch.bfloat16)
+    wf = torch.stack([hi, (flat - hi.float()).to(torch.bfloat16)], 0) if split else hi
     conv.__dict__["_sb_pack_patches"] = (key, wf)
     return wf
 
@@ -64,13 +80,14 @@ def prepack(model):
              m.kernel_size[0] * m.kernel_size[1] <= ops.MAX_TAPS]
     if not convs:
         return
-    keys = [(c.weight._version, c.weight.data_ptr(), True) for c in convs]
+    split = precision.split_enabled()
+    keys = [(c.weight._version, c.weight.data_ptr(), True, split) for c in convs]
     if all(c.__dict__.get("_sb_pack", (None,))[0] == k for c, k in zip(convs, keys)):
         return                                            # nothing changed since the last pack
     plan = model.__dict__.get("_sb_pack_plan")
     weights = [c.weight.detach() for c in convs]
-    if plan is None or not plan.valid_for(weights):
-        plan = ops.WeightPackPlan(weights)
+    if plan is None or not plan.valid_for(weights, split):
+        plan = ops.WeightPackPlan(weights, split)
         model.__dict__["_sb_pack_plan"] = plan
     plan.refresh()
     for c, k, pw in zip(convs, keys, plan.packs):
@@ -112,7 +129,7 @@ def _bn_backward(ctx_pg, world, dy, y, raw, mi, gamma, relu, want_dres, ss=None)
     """Shared BN(+ReLU) backward: returns (d_raw, dres, dgamma, dbeta). The ReLU mask comes from the saved output `y`,
     or — when `y` is None and `ss` (scale/shift) is given, i.e. no residual — is recomputed from `raw` (saves one
     tensor read in each of the two passes)."""
-    n, h, w, c = raw.shape
+    n, h, w, c = raw.shape[-4:]
     if not dy.is_contiguous():
         dy = dy.contiguous()
     px = p2p.get_exchange(ctx_pg) if ctx_pg is not None else None
@@ -146,9 +163,10 @@ def cba_forward(x, conv, bn, relu, residual, out=None, input_needs_grad=True):
     Stride-2 convs (stem conv1, layer2.0 conv2 / downsample — model/resnet.py:108,130-137) run on the same
     stride-1 tensor-core kernel through a 2x2 phase decomposition of the input (ops.space_to_phases): tap (r, s)
     reads phase ((r+1)&1, (s+1)&1) shifted by -1 or 0; dgrad is one small conv per phase, wgrad reads the phases."""
-    pw = packed(conv)
+    split = ops.is_split(x)
+    pw = packed(conv, split=split)
     k, dil, stride = conv.kernel_size[0], conv.dilation[0], conv.stride[0]
-    n, h, w, cx = x.shape
+    n, h, w, cx = x.shape[-4:]
     wf = pw.wf
     if stride == 1:
         xin, img_add, out_nhw = x, None, None
@@ -156,7 +174,7 @@ def cba_forward(x, conv, bn, relu, residual, out=None, input_needs_grad=True):
     elif not input_needs_grad and _is_patch_conv(conv, x):
         # stem conv: one 1x1 conv over 27-value input patches instead of 9 taps of a 3(->64)-channel K block
         xin, img_add, out_nhw = ops.im2col3x3s2(x, conv.in_channels), None, None
-        taps, wf, stride = ops.conv_taps(1, 1), packed_patches(conv), 0       # stride 0 marks the patch form
+        taps, wf, stride = ops.conv_taps(1, 1), packed_patches(conv, split), 0    # stride 0 marks the patch form
     else:
         xin = ops.space_to_phases(x)                     # [4N, Hh, Wh, C]
         t2 = ops.conv_taps_s2(k, n)
@@ -221,20 +239,21 @@ def cba_backward(st, dy, need_dx=True, need_dw=True, need_dres=False, dx_add=Non
         if need_dx:
             if pw.cin % 64 != 0:
                 raise NotImplementedError("semseg_b200: input gradient of a stride-2 conv needs Cin % 64 == 0")
-            hh, wh = st.xin.shape[1], st.xin.shape[2]
-            dxp = torch.empty((4 * n, hh, wh, pw.cin), dtype=torch.bfloat16, device=dy.device)
+            hh, wh = st.xin.shape[-3], st.xin.shape[-2]
+            dxp = ops.empty_act((4 * n, hh, wh, pw.cin), ops.is_split(d_raw), dy.device)
             for q in range(4):
                 sub = [(-t[0], -t[1], t[2]) for t in t2 if t[4] == (q >> 1, q & 1)]
+                part = ops.act_batch_slice(dxp, q * n, (q + 1) * n)
                 if sub:      # dx of phase q: conv of d_raw with the taps that read this phase (mirrored shifts)
-                    ops.conv_fprop(d_raw, pw.wd, pw.cin, sub, out=dxp[q * n:(q + 1) * n], out_nhw=(n, hh, wh))
+                    ops.conv_fprop(d_raw, pw.wd, pw.cin, sub, out=part, out_nhw=(n, hh, wh))
                 else:
-                    dxp[q * n:(q + 1) * n].zero_()
+                    part.zero_()
             dx = ops.phases_to_space(dxp, n, h, w)
             if dx_add is not None:
-                dx = ops.add_bf16(dx, dx_add)
+                dx = ops.add_act(dx, dx_add)
         if need_dw:
             dw = ops.conv_wgrad(st.xin, d_raw, cx, pw.cout, [t[:2] for t in t2], img_add=[t[3] for t in t2])
-    if dw is not None and cx != pw.cin:
+    if dw is not None and cx != pw.cin and st.stride != 0:
         dw = dw[:, :pw.cin].contiguous()          # input channels were zero-padded to a multiple of 8 (stem)
     return dx, dw, dgamma, dbeta, dres
 
@@ -314,28 +333,6 @@ def bottleneck(x, blk):
     return conv_bn_act(y, blk.conv3, blk.bn3, relu=True, residual=residual)
 
 
-class _BnAct(torch.autograd.Function):
-    """Training BatchNorm + optional residual + optional ReLU on a raw NHWC bf16 tensor."""
-
-    @staticmethod
-    def forward(ctx, raw, gamma, beta, residual, bn, relu):
-        stats = ops.bn_stats(raw)
-        pg = _sync_group(bn)
-        mi, ss, world = _finalize_stats(stats, bn, pg)
-        y = ops.bn_apply(raw, ss, residual=residual, relu=relu)
-        need_y = relu and residual is not None
-        ctx.save_for_backward(raw, y if need_y else None, mi, gamma, ss if (relu and not need_y) else None)
-        ctx.relu, ctx.pg, ctx.world, ctx.has_res = relu, pg, world, residual is not None
-        return y
-
-    @staticmethod
-    def backward(ctx, dy):
-        raw, y, mi, gamma, ss = ctx.saved_tensors
-        d_raw, dres, dgamma, dbeta = _bn_backward(ctx.pg, ctx.world, dy, y, raw, mi, gamma, ctx.relu,
-                                                  ctx.has_res and ctx.needs_input_grad[3], ss)
-        return d_raw, dgamma, dbeta, dres, None, None
-
-
 def _is_native_conv(conv, cin):
     """Convs the tensor-core kernel covers: 1x1 / 3x3 'same' convs, stride 1 (any dilation) or stride 2 (dilation 1)."""
     ok = (conv.kernel_size in ((1, 1), (3, 3)) and conv.groups == 1 and conv.bias is None and
@@ -346,46 +343,38 @@ def _is_native_conv(conv, cin):
     return ok and conv.stride == (2, 2) and conv.dilation == (1, 1)
 
 
-def _library_conv(x, conv):
-    """cuDNN channels-last bf16 path for convolutions outside the kernel's coverage (none in PSPNet / PSANet: every
-    conv of the reference networks, including the stride-2 ones, runs on the tensor-core kernel)."""
-    xn = x.permute(0, 3, 1, 2)  # NCHW view of the NHWC buffer (= channels_last)
-    if xn.shape[1] != conv.in_channels:
-        xn = xn[:, :conv.in_channels]
-    y = F.conv2d(xn, conv.weight.to(torch.bfloat16), None, conv.stride, conv.padding, conv.dilation, conv.groups)
-    return y.permute(0, 2, 3, 1).contiguous()
+def _require_native(conv, cin):
+    """There is exactly one backend: a convolution the sm_100a kernel does not cover is an error, never a library
+    (cuDNN) fallback. Every convolution of PSPNet / PSANet (model/resnet.py, model/pspnet.py, model/psanet.py) is covered."""
+    if not _is_native_conv(conv, cin):
+        raise NotImplementedError(
+            "semseg_b200: convolution %r on %d input channels is outside the tensor-core kernel's coverage (1x1 / 3x3 "
+            "'same' convs without bias, stride 1 with any dilation or stride 2 undilated, Cin %% 8 == 0, Cout %% 64 == 0); "
+            "there is no library fallback" % (conv, cin))
 
 
 def conv_bn_act(x, conv, bn, relu=True, residual=None, out=None):
-    """NHWC bf16 -> NHWC bf16: conv -> BatchNorm -> (+residual) -> (ReLU), training or eval semantics of `bn`."""
+    """NHWC activation -> NHWC activation: conv -> BatchNorm -> (+residual) -> (ReLU), training or eval semantics of `bn`."""
     use_batch_stats = bn.training or (bn.running_mean is None)
-    native = _is_native_conv(conv, x.shape[-1])
-    if not use_batch_stats:
-        ss = ops.bn_fold_eval(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-        if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
-            raise NotImplementedError("semseg_b200: gradients through eval-mode BatchNorm are not supported; "
-                                      "run eval under torch.no_grad()")
-        if native:
-            pw = packed(conv, need_dgrad=False)
-            if conv.stride == (1, 1):
-                y, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(conv.kernel_size[0], conv.dilation[0]),
-                                      epi=EPI_AFFINE, relu=relu, scale=ss[0], shift=ss[1], residual=residual, out=out)
-            else:
-                n, h, w, _ = x.shape
-                t2 = ops.conv_taps_s2(conv.kernel_size[0], n)
-                y, _ = ops.conv_fprop(ops.space_to_phases(x), pw.wf, pw.cout, [t[:3] for t in t2], epi=EPI_AFFINE,
-                                      relu=relu, scale=ss[0], shift=ss[1], residual=residual, out=out,
-                                      img_add=[t[3] for t in t2], out_nhw=(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1))
-            return y
-        raw = _library_conv(x, conv)
-        return ops.bn_apply(raw, ss, residual=residual, relu=relu, out=out)
-    if native:
+    _require_native(conv, x.shape[-1])
+    if use_batch_stats:
         return _ConvBnAct.apply(x, conv.weight, bn.weight, bn.bias, residual, conv, bn, relu, out)
-    raw = _library_conv(x, conv)
-    y = _BnAct.apply(raw, bn.weight, bn.bias, residual, bn, relu)
-    if out is not None:
-        out.copy_(y)
-        return out
+    # Eval-mode BatchNorm: conv + folded BN + residual + ReLU are ONE kernel. It has no backward: the reference's
+    # validate() (tool/train.py:353-359) calls model.eval()(input) without torch.no_grad() and never back-propagates,
+    # so the result is returned detached (a later .backward() through it raises torch's usual "does not require grad").
+    ss = ops.bn_fold_eval(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+    split = ops.is_split(x)
+    with torch.no_grad():
+        pw = packed(conv, need_dgrad=False, split=split)
+        if conv.stride == (1, 1):
+            y, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(conv.kernel_size[0], conv.dilation[0]),
+                                  epi=EPI_AFFINE, relu=relu, scale=ss[0], shift=ss[1], residual=residual, out=out)
+        else:
+            n, h, w, _ = x.shape[-4:]
+            t2 = ops.conv_taps_s2(conv.kernel_size[0], n)
+            y, _ = ops.conv_fprop(ops.space_to_phases(x), pw.wf, pw.cout, [t[:3] for t in t2], epi=EPI_AFFINE,
+                                  relu=relu, scale=ss[0], shift=ss[1], residual=residual, out=out,
+                                  img_add=[t[3] for t in t2], out_nhw=(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1))
     return y
 
 
@@ -395,7 +384,7 @@ class _ConvBiasF32(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, conv):
-        pw = packed(conv)
+        pw = packed(conv, split=ops.is_split(x))
         y, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(1, 1), epi=EPI_F32, shift=bias)
         ctx.save_for_backward(x)
         ctx.pw = pw
@@ -406,9 +395,8 @@ class _ConvBiasF32(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         pw = ctx.pw
         n, h, w, c = dy.shape
-        cp = pw.wd.shape[2]  # Cout rounded up to 8 (zero padded operand)
-        dyb = torch.zeros((n, h, w, cp), dtype=torch.bfloat16, device=dy.device)
-        dyb[..., :c] = dy
+        cp = pw.wd.shape[-1]  # Cout rounded up to 8 (zero padded operand)
+        dyb = ops.f32_to_act(dy.contiguous(), ops.is_split(x))      # [N,h,w,cp], padding columns zero
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx, _ = ops.conv_fprop(dyb, pw.wd, pw.cin, ops.conv_taps(1, 1))
@@ -424,7 +412,7 @@ def conv_bias_f32(x, conv):
     assert conv.kernel_size == (1, 1) and conv.stride == (1, 1) and x.shape[-1] % 8 == 0
     if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
         return _ConvBiasF32.apply(x, conv.weight, conv.bias, conv)
-    pw = packed(conv, need_dgrad=False)
+    pw = packed(conv, need_dgrad=False, split=ops.is_split(x))
     y, _ = ops.conv_fprop(x, pw.wf, pw.cout, ops.conv_taps(1, 1), epi=EPI_F32, shift=conv.bias)
     return y
 
@@ -480,7 +468,7 @@ class _PPMPool(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, bins, link):
-        ctx.bins, ctx.shape, ctx.link = bins, tuple(x.shape), link
+        ctx.bins, ctx.shape, ctx.link = bins, tuple(x.shape[-4:]), link
         return tuple(ops.ppm_pool(x, bins))
 
     @staticmethod
@@ -526,17 +514,96 @@ def ppm_link():
 
 # ------------------------------------------------------------------------------------------------ misc NHWC ops
 def to_nhwc_bf16(x_nchw):
-    """fp32 NCHW module input -> bf16 NHWC (channels padded to a multiple of 8 with zeros)."""
-    return ops.nchw_to_nhwc_bf16(x_nchw.contiguous().float())
+    """fp32 NCHW module input -> NHWC activation (channels padded to a multiple of 8 with zeros) in the storage form of
+    the current precision mode (precision.py): plain bf16, or (hi, lo) bf16 planes for bf16x3."""
+    return ops.nchw_to_nhwc_bf16(x_nchw.contiguous().float(), split=precision.split_enabled())
+
+
+class _ActToF32(torch.autograd.Function):
+    """activation -> fp32 NHWC (differentiable)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.split = ops.is_split(x)
+        return ops.act_to_f32(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.f32_to_act(dy.contiguous(), ctx.split)
+
+
+class _F32ToAct(torch.autograd.Function):
+    """fp32 NHWC -> activation in the requested storage form (differentiable)."""
+
+    @staticmethod
+    def forward(ctx, x, split):
+        return ops.f32_to_act(x.contiguous(), split)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.act_to_f32(dy.contiguous()), None
+
+
+def act_to_f32(x):
+    return _ActToF32.apply(x)
+
+
+def f32_to_act(x, split):
+    return _F32ToAct.apply(x, split)
+
+
+def to_nchw_f32(y):
+    """NHWC activation -> fp32 NCHW (what the reference's modules return)."""
+    if not (torch.is_grad_enabled() and y.requires_grad):
+        return ops.nhwc_bf16_to_nchw(y)
+    return act_to_f32(y).permute(0, 3, 1, 2)
+
+
+class _Fork(torch.autograd.Function):
+    """x -> k aliases of x whose gradients are summed by the split-aware add kernel (autograd's own accumulation would
+    add the hi and lo planes of two split gradients separately, losing the error compensation)."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        return tuple(x.view_as(x) for _ in range(k))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        acc = None
+        for g in grads:
+            if g is None:
+                continue
+            g = g if g.is_contiguous() else g.contiguous()
+            acc = g if acc is None else ops.add_act(acc, g)
+        return acc, None
+
+
+def fork(x, k=2):
+    """k handles on x for k consumers (gradient fan-in through one native add per extra branch)."""
+    if not (torch.is_grad_enabled() and x.requires_grad):
+        return (x,) * k
+    return _Fork.apply(x, k)
+
+
+class _ScaleNC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.save_for_backward(scale)
+        return ops.scale_nc(x, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (scale,) = ctx.saved_tensors
+        return ops.scale_nc(dy if dy.is_contiguous() else dy.contiguous(), scale), None
 
 
 def dropout2d_nhwc(x, p, training):
-    """nn.Dropout2d on NHWC: one Bernoulli per (n, c) (model/pspnet.py:68,76)."""
+    """nn.Dropout2d on NHWC: one Bernoulli per (n, c), kept channels scaled by 1/(1-p) (model/pspnet.py:68,76)."""
     if not training or p == 0.0:
         return x
-    n, _, _, c = x.shape
-    keep = torch.empty((n, 1, 1, c), device=x.device, dtype=torch.float32).bernoulli_(1.0 - p)
-    return x * (keep / (1.0 - p)).to(x.dtype)
+    n, c = x.shape[-4], x.shape[-1]
+    scale = torch.empty((n, c), device=x.device, dtype=torch.float32).bernoulli_(1.0 - p).mul_(1.0 / (1.0 - p))
+    return _ScaleNC.apply(x, scale)
 
 
 class _MaxPool3x3s2(torch.autograd.Function):
@@ -544,7 +611,7 @@ class _MaxPool3x3s2(torch.autograd.Function):
     def forward(ctx, x):
         y, code = ops.maxpool3x3s2_fwd(x, want_argcode=True)
         ctx.save_for_backward(code)
-        ctx.in_shape = tuple(x.shape)
+        ctx.in_shape = tuple(x.shape[-4:])
         return y
 
     @staticmethod
@@ -561,6 +628,5 @@ def maxpool_nhwc(x, pool):
     if (_pair(pool.kernel_size) == (3, 3) and _pair(pool.stride) == (2, 2) and _pair(pool.padding) == (1, 1)
             and _pair(pool.dilation) == (1, 1) and not pool.ceil_mode and x.shape[-1] % 8 == 0):
         return _MaxPool3x3s2.apply(x)
-    xn = x.permute(0, 3, 1, 2)
-    y = F.max_pool2d(xn, pool.kernel_size, pool.stride, pool.padding, pool.dilation, pool.ceil_mode)
-    return y.permute(0, 2, 3, 1).contiguous()
+    raise NotImplementedError("semseg_b200: only MaxPool2d(kernel_size=3, stride=2, padding=1) (model/resnet.py:115) is "
+                              "implemented; there is no library fallback (got %r)" % (pool,))

@@ -10,6 +10,9 @@ from . import _lib
 from ._lib import ConvDesc, WgradDesc, EPI_RAW, EPI_AFFINE, EPI_F32, MAX_TAPS
 
 
+# bf16x3: K blocks (64-channel block x tap) one tensor-core accumulation chain may span (21 x 4 x 3 = 252 MMA steps)
+X3_MAX_KBLOCKS = 21
+
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 _cur_device = getattr(torch._C, "_cuda_getDevice", None)
 
@@ -33,13 +36,51 @@ def _require_cuda(*ts):
             raise _lib.SemsegError("semseg_b200 ops require CUDA tensors (no CPU fallback); got device %s" % t.device)
 
 
+# ------------------------------------------------------------------------------------------------ activation storage
+# An activation is either a plain bf16 NHWC tensor [N,H,W,C] ("bf16", the speed configuration) or a SPLIT tensor
+# [2,N,H,W,C]: plane 0 = hi = bf16(v), plane 1 = lo = bf16(v - hi) (16 mantissa bits, csrc/act.cuh). The conv kernels
+# consume split operands as three K segments (bf16x3); every other kernel reads hi + lo and re-splits its result. The
+# storage form is chosen once per model call (precision.py) and every op follows the form of its input.
+def is_split(t):
+    return t is not None and t.dim() == 5
+
+
 def _nhwc_meta(t):
-    """(N, H, W, C, pitch) of a bf16 NHWC tensor whose channel dim may be a slice of a wider buffer."""
-    assert t.dim() == 4 and t.dtype == torch.bfloat16, (t.shape, t.dtype)
-    n, h, w, c = t.shape
-    sn, sh, sw, sc = t.stride()
+    """(N, H, W, C, pitch) of a bf16 NHWC activation (plain 4-D or split 5-D) whose channel dim may be a slice of a
+    wider buffer."""
+    assert t.dtype == torch.bfloat16 and t.dim() in (4, 5), (t.shape, t.dtype)
+    if t.dim() == 5:
+        assert t.shape[0] == 2, "split activation must be [2,N,H,W,C] (hi, lo planes)"
+    n, h, w, c = t.shape[-4:]
+    sn, sh, sw, sc = t.stride()[-4:]
     assert sc == 1 and sh == sw * w and sn == sh * h, "NHWC tensor must be pixel-contiguous (stride %s)" % (t.stride(),)
     return n, h, w, c, sw
+
+
+def _lo(t):
+    """Pointer to the lo plane of a split activation, NULL for a plain one."""
+    if t is not None and t.dim() == 5:
+        return ctypes.c_void_p(t.data_ptr() + 2 * t.stride(0))
+    return ctypes.c_void_p(0)
+
+
+def _lo_int(t):
+    return t.data_ptr() + 2 * t.stride(0) if (t is not None and t.dim() == 5) else 0
+
+
+def empty_act(shape, split, device):
+    """Uninitialised activation of NHWC shape `shape` in the requested storage form."""
+    return torch.empty(((2,) + tuple(shape)) if split else tuple(shape), dtype=torch.bfloat16, device=device)
+
+
+def _same_form(*ts):
+    forms = {t.dim() == 5 for t in ts if t is not None}
+    assert len(forms) <= 1, "activations of one call must all be plain or all be split"
+
+
+def act_batch_slice(t, a, b):
+    """Images a..b of an activation (either storage form)."""
+    return t[:, a:b] if t.dim() == 5 else t[a:b]
 
 
 def round_up(a, b):
@@ -71,14 +112,19 @@ def psamask_bwd(grad_out, psa_type, mask_h, mask_w):
 
 # ------------------------------------------------------------------------------------------------ weights
 class PackedWeight:
-    """bf16 operand slabs of one conv weight: wf [taps][Cout][Cin_p] (fprop), wd [taps][Cin][Cout_p] (dgrad)."""
-    __slots__ = ("wf", "wd", "cout", "cin", "taps", "ksize")
+    """bf16 operand slabs of one conv weight: wf [taps][Cout][Cin_p] (fprop), wd [taps][Cin][Cout_p] (dgrad); with
+    split=True each is [2][taps][rows][cols] = the hi slab followed by the lo slab (bf16x3 operand mode)."""
+    __slots__ = ("wf", "wd", "cout", "cin", "taps", "ksize", "split")
 
-    def __init__(self, wf, wd, cout, cin, taps, ksize):
-        self.wf, self.wd, self.cout, self.cin, self.taps, self.ksize = wf, wd, cout, cin, taps, ksize
+    def __init__(self, wf, wd, cout, cin, taps, ksize, split=False):
+        self.wf, self.wd, self.cout, self.cin, self.taps, self.ksize, self.split = wf, wd, cout, cin, taps, ksize, split
 
 
-def pack_weights(w, need_dgrad=True):
+def _slab(taps, rows, cols, split, device):
+    return torch.empty(((2,) if split else ()) + (taps, rows, cols), dtype=torch.bfloat16, device=device)
+
+
+def pack_weights(w, need_dgrad=True, split=False):
     """w: fp32 OIHW parameter -> PackedWeight (one fused launch pair)."""
     _require_cuda(w)
     lib = _lib.load()
@@ -90,12 +136,13 @@ def pack_weights(w, need_dgrad=True):
     assert kh == kw
     taps = kh * kw
     cin_p, cout_p = round_up(cin, 8), round_up(cout, 8)
-    wf = torch.empty((taps, cout, cin_p), dtype=torch.bfloat16, device=w.device)
-    wd = torch.empty((taps, cin, cout_p), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
+    wf = _slab(taps, cout, cin_p, split, w.device)
+    wd = _slab(taps, cin, cout_p, split, w.device) if need_dgrad else None
     _lib.check(lib.semseg_pack_weights(_ptr(w), cout, cin, taps, _ptr(wf), cout, cin_p, _ptr(wd),
-                                       cin if need_dgrad else 0, cout_p if need_dgrad else 0, _stream()),
+                                       cin if need_dgrad else 0, cout_p if need_dgrad else 0, int(bool(split)),
+                                       _stream()),
                "semseg_pack_weights")
-    return PackedWeight(wf, wd, cout, cin, taps, kh)
+    return PackedWeight(wf, wd, cout, cin, taps, kh, bool(split))
 
 
 class WeightPackPlan:
@@ -105,9 +152,10 @@ class WeightPackPlan:
     model needs new slabs, which costs 2 launches per conv on the per-layer path. The plan owns one (wf, wd) pair per
     conv and a device-side item table; `refresh()` re-packs all of them into the same buffers."""
 
-    def __init__(self, weights):
+    def __init__(self, weights, split=False):
         import ctypes
         _require_cuda(*weights)
+        self.split = bool(split)
         self.weights = [w for w in weights]
         self.ptrs = [w.data_ptr() for w in weights]
         self.packs = []
@@ -119,21 +167,22 @@ class WeightPackPlan:
             taps = kh * kh
             assert taps <= MAX_TAPS
             cin_p, cout_p = round_up(cin, 8), round_up(cout, 8)
-            wf = torch.empty((taps, cout, cin_p), dtype=torch.bfloat16, device=w.device)
-            wd = torch.empty((taps, cin, cout_p), dtype=torch.bfloat16, device=w.device)
-            self.packs.append(PackedWeight(wf, wd, cout, cin, taps, kh))
+            wf = _slab(taps, cout, cin_p, self.split, w.device)
+            wd = _slab(taps, cin, cout_p, self.split, w.device)
+            self.packs.append(PackedWeight(wf, wd, cout, cin, taps, kh, self.split))
             it = items[k]
             it.w, it.wf, it.wd = w.data_ptr(), wf.data_ptr(), wd.data_ptr()
             it.Cout, it.Cin, it.taps, it.cols_f, it.cols_d = cout, cin, taps, cin_p, cout_p
-            it.tile0, it.tiles_ci = tile0, (cin_p + 31) // 32
+            it.tile0, it.tiles_ci, it.split = tile0, (cin_p + 31) // 32, int(self.split)
             tile0 += it.tiles_ci * ((cout_p + 31) // 32)
             max_taps = max(max_taps, taps)
         self.n_items, self.n_tiles, self.max_taps = len(weights), tile0, max_taps
         raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8)
         self.items_dev = raw.to(weights[0].device)
 
-    def valid_for(self, weights):
-        return len(weights) == len(self.ptrs) and all(w.data_ptr() == p for w, p in zip(weights, self.ptrs))
+    def valid_for(self, weights, split=False):
+        return (bool(split) == self.split and len(weights) == len(self.ptrs) and
+                all(w.data_ptr() == p for w, p in zip(weights, self.ptrs)))
 
     def refresh(self):
         lib = _lib.load()
@@ -180,12 +229,21 @@ def conv_taps_s2(ksize, n):
     return taps
 
 
+def _planes(*ts):
+    """[(plane views...)] of activations that share a storage form: one tuple for plain tensors, two for split."""
+    _same_form(*ts)
+    if ts[0].dim() == 5:
+        return [tuple(t[0] for t in ts), tuple(t[1] for t in ts)]
+    return [tuple(ts)]
+
+
 def im2col3x3s2(x, cin):
     """NHWC bf16 x (first `cin` <= 3 channels real) -> patches [N, Ho, Wo, 32] of the 3x3 / stride 2 / pad 1 stem conv."""
     lib = _lib.load()
     n, h, w, _, p = _nhwc_meta(x)
-    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 32), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.semseg_im2col3x3s2(_ptr(x), p, n, h, w, int(cin), _ptr(out), _stream()), "semseg_im2col3x3s2")
+    out = empty_act((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 32), is_split(x), x.device)
+    for xi, oi in _planes(x, out):      # pure data movement: the hi and lo planes are gathered independently
+        _lib.check(lib.semseg_im2col3x3s2(_ptr(xi), p, n, h, w, int(cin), _ptr(oi), _stream()), "semseg_im2col3x3s2")
     return out
 
 
@@ -194,17 +252,19 @@ def space_to_phases(x):
     _require_cuda(x)
     lib = _lib.load()
     n, h, w, c, p = _nhwc_meta(x)
-    xp = torch.empty((4 * n, (h + 1) // 2, (w + 1) // 2, c), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.semseg_space_to_phases(_ptr(x), p, n, h, w, c, _ptr(xp), _stream()), "semseg_space_to_phases")
+    xp = empty_act((4 * n, (h + 1) // 2, (w + 1) // 2, c), is_split(x), x.device)
+    for xi, oi in _planes(x, xp):
+        _lib.check(lib.semseg_space_to_phases(_ptr(xi), p, n, h, w, c, _ptr(oi), _stream()), "semseg_space_to_phases")
     return xp
 
 
 def phases_to_space(xp, n, h, w):
     lib = _lib.load()
     c = xp.shape[-1]
-    assert xp.is_contiguous() and xp.shape[0] == 4 * n
-    x = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=xp.device)
-    _lib.check(lib.semseg_phases_to_space(_ptr(xp), n, h, w, c, _ptr(x), _stream()), "semseg_phases_to_space")
+    assert xp.is_contiguous() and xp.shape[-4] == 4 * n
+    x = empty_act((n, h, w, c), is_split(xp), xp.device)
+    for xi, oi in _planes(xp, x):
+        _lib.check(lib.semseg_phases_to_space(_ptr(xi), n, h, w, c, _ptr(oi), _stream()), "semseg_phases_to_space")
     return x
 
 
@@ -223,12 +283,16 @@ def conv_fprop(x, w3d, cout, taps, *, out=None, epi=EPI_RAW, relu=False, scale=N
     _require_cuda(x, w3d)
     lib = _lib.load()
     nin, hin, win, cin, xp = _nhwc_meta(x)
+    split = is_split(x)
     n, h, w = out_nhw if out_nhw is not None else (nin, hin, win)   # output pixel grid (differs for phase tensors)
     d = ConvDesc()
     d.N, d.H, d.W, d.Cin, d.Cout = n, h, w, cin, cout
     d.x, d.Nin, d.Hin, d.Win, d.x_pitch = x.data_ptr(), nin, hin, win, xp
-    assert w3d.dtype == torch.bfloat16 and w3d.is_contiguous() and w3d.dim() == 3
-    d.w, d.n_wtaps, d.w_rows, d.w_cols = w3d.data_ptr(), w3d.shape[0], w3d.shape[1], w3d.shape[2]
+    d.x_lo = _lo_int(x)
+    assert w3d.dtype == torch.bfloat16 and w3d.is_contiguous() and w3d.dim() == (4 if split else 3), \
+        "packed weights must be [taps][rows][cols] (plain) or [2][taps][rows][cols] (split, hi then lo slab)"
+    d.w, d.n_wtaps, d.w_rows, d.w_cols = w3d.data_ptr(), w3d.shape[-3], w3d.shape[-2], w3d.shape[-1]
+    d.w_split = int(split)
     _fill_taps(d, taps, img_add=img_add)
     d.epi_mode, d.relu = epi, int(bool(relu))
     sp = None
@@ -240,10 +304,10 @@ def conv_fprop(x, w3d, cout, taps, *, out=None, epi=EPI_RAW, relu=False, scale=N
         y = out_f32
     else:
         if out is None:
-            out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x.device)
+            out = empty_act((n, h, w, cout), split, x.device)
         on, oh, ow, oc, op = _nhwc_meta(out)
-        assert (on, oh, ow, oc) == (n, h, w, cout)
-        d.y, d.y_pitch = out.data_ptr(), op
+        assert (on, oh, ow, oc) == (n, h, w, cout) and is_split(out) == split
+        d.y, d.y_pitch, d.y_lo = out.data_ptr(), op, _lo_int(out)
         y = out
     if scale is not None:
         assert scale.dtype == torch.float32 and scale.numel() >= cout
@@ -253,8 +317,27 @@ def conv_fprop(x, w3d, cout, taps, *, out=None, epi=EPI_RAW, relu=False, scale=N
         d.shift = shift.data_ptr()
     if residual is not None:
         rn, rh, rw, rc, rp = _nhwc_meta(residual)
-        assert (rn, rh, rw, rc) == (n, h, w, cout)
-        d.residual, d.res_pitch = residual.data_ptr(), rp
+        assert (rn, rh, rw, rc) == (n, h, w, cout) and is_split(residual) == split
+        d.residual, d.res_pitch, d.residual_lo = residual.data_ptr(), rp, _lo_int(residual)
+    # bf16x3: convs with long K are K-sliced (fp32 partials summed round-to-nearest by conv_splitk_finish), because one
+    # tensor-core accumulation chain loses ~2^-24 per MMA step towards zero (tools/probe_accum.py)
+    k_slices = int(lib.semseg_conv_k_slices(cin, len(taps), X3_MAX_KBLOCKS)) if (split and epi != EPI_F32) else 1
+    if k_slices > 1:
+        part = torch.empty((k_slices, n, h, w, cout), dtype=torch.float32, device=x.device)
+        d.epi_mode, d.relu = EPI_F32, 0
+        d.out_f32, d.out_pitch = part.data_ptr(), cout
+        d.k_slices, d.slice_stride = k_slices, part.stride(0)
+        sc, sh, rs, rsl, rpitch, ylo = d.scale, d.shift, d.residual, d.residual_lo, d.res_pitch, d.y_lo
+        d.scale = d.shift = d.residual = d.residual_lo = d.y_lo = None
+        _lib.check(lib.semseg_conv_fprop(ctypes.byref(d), _stream()), "semseg_conv_fprop (K-sliced)")
+        m = n * h * w
+        if stats:
+            assert epi == EPI_RAW
+            sp = torch.empty((int(lib.semseg_conv_splitk_rows(m)), 3, cout), dtype=torch.float32, device=x.device)
+        _lib.check(lib.semseg_conv_splitk_finish(_ptr(part), k_slices, part.stride(0), cout, m, cout, epi,
+                                                 int(bool(relu)), sc, sh, rs, rsl, rpitch, d.y, ylo, d.y_pitch,
+                                                 _ptr(sp), _stream()), "semseg_conv_splitk_finish")
+        return y, sp
     if stats:
         assert epi == EPI_RAW
         sp = torch.empty((conv_stats_rows(n, h, w, cout), 3, cout), dtype=torch.float32, device=x.device)
@@ -272,10 +355,12 @@ def conv_wgrad(x, dy, cin, cout, taps, grad_out=None, accumulate=False, img_add=
     n, h, w, dc, dp = _nhwc_meta(dy)
     assert xc >= cin and dc >= cout
     assert img_add is not None or (nin, hin, win) == (n, h, w)
+    _same_form(x, dy)
     d = WgradDesc()
     d.N, d.H, d.W, d.Cin, d.Cout = n, h, w, cin, cout
     d.x, d.Nin, d.Hin, d.Win, d.x_pitch = x.data_ptr(), nin, hin, win, xp
     d.dy, d.dy_pitch = dy.data_ptr(), dp
+    d.x_lo, d.dy_lo = _lo_int(x), _lo_int(dy)
     _fill_taps(d, taps, with_wtap=False, img_add=img_add)
     d.n_splits = 0
     splits = lib.semseg_conv_wgrad_splits(ctypes.byref(d))
@@ -297,14 +382,15 @@ def conv_wgrad(x, dy, cin, cout, taps, grad_out=None, accumulate=False, img_add=
 
 
 # ------------------------------------------------------------------------------------------------ layout
-def nchw_to_nhwc_bf16(x, pad_to=8):
+def nchw_to_nhwc_bf16(x, pad_to=8, split=False):
     _require_cuda(x)
     lib = _lib.load()
     assert x.dtype == torch.float32 and x.is_contiguous()
     n, c, h, w = x.shape
     cp = round_up(c, pad_to)
-    out = (torch.zeros if cp != c else torch.empty)((n, h, w, cp), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.semseg_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(out), n, c, h, w, cp, _stream()),
+    shape = ((2,) if split else ()) + (n, h, w, cp)
+    out = (torch.zeros if cp != c else torch.empty)(shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.semseg_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(out), _lo(out), n, c, h, w, cp, _stream()),
                "semseg_nchw_f32_to_nhwc_bf16")
     return out
 
@@ -314,7 +400,7 @@ def nhwc_bf16_to_nchw(x):
     lib = _lib.load()
     n, h, w, c, p = _nhwc_meta(x)
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
-    _lib.check(lib.semseg_nhwc_bf16_to_nchw_f32(_ptr(x), _ptr(out), n, c, h, w, p, _stream()),
+    _lib.check(lib.semseg_nhwc_bf16_to_nchw_f32(_ptr(x), _lo(x), _ptr(out), n, c, h, w, p, _stream()),
                "semseg_nhwc_bf16_to_nchw_f32")
     return out
 
@@ -398,15 +484,17 @@ def bn_apply(x, scale_shift, residual=None, relu=True, out=None):
     lib = _lib.load()
     n, h, w, c, xp = _nhwc_meta(x)
     if out is None:
-        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+        out = empty_act((n, h, w, c), is_split(x), x.device)
     _, _, _, oc, op = _nhwc_meta(out)
     assert oc == c
     rp = 0
     if residual is not None:
         _, _, _, rc, rp = _nhwc_meta(residual)
         assert rc == c
-    _lib.check(lib.semseg_bn_apply(_ptr(x), xp, _ptr(scale_shift), _ptr(residual), rp, _ptr(out), op, n * h * w, c,
-                                   int(bool(relu)), _stream()), "semseg_bn_apply")
+    _same_form(x, out, residual)
+    _lib.check(lib.semseg_bn_apply(_ptr(x), _lo(x), xp, _ptr(scale_shift), _ptr(residual), _lo(residual), rp,
+                                   _ptr(out), _lo(out), op, n * h * w, c, int(bool(relu)), _stream()),
+               "semseg_bn_apply")
     return out
 
 
@@ -418,8 +506,10 @@ def bn_bwd_reduce(dy, y, x, mean_invstd, relu, scale_shift=None):
     m = n * h * w
     ws, nf = bn_workspace(m, c, dy.device)
     sums = torch.empty((2, c), dtype=torch.float32, device=dy.device)
-    _lib.check(lib.semseg_bn_bwd_reduce(_ptr(dy), dp, _ptr(y), yp, _ptr(x), xp, _ptr(mean_invstd), _ptr(scale_shift),
-                                        m, c, int(bool(relu)), _ptr(ws), nf, _ptr(sums), _stream()),
+    _same_form(dy, y, x)
+    _lib.check(lib.semseg_bn_bwd_reduce(_ptr(dy), _lo(dy), dp, _ptr(y), _lo(y), yp, _ptr(x), _lo(x), xp,
+                                        _ptr(mean_invstd), _ptr(scale_shift), m, c, int(bool(relu)), _ptr(ws), nf,
+                                        _ptr(sums), _stream()),
                "semseg_bn_bwd_reduce")
     return sums
 
@@ -430,34 +520,65 @@ def bn_bwd_apply(dy, y, x, mean_invstd, gamma, sums, count, relu, want_dres=Fals
     n, h, w, c, dp = _nhwc_meta(dy)
     _, _, _, _, xp = _nhwc_meta(x)
     yp = _nhwc_meta(y)[4] if y is not None else 0
-    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
-    dres = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device) if want_dres else None
+    _same_form(dy, y, x)
+    split = is_split(dy)
+    dx = empty_act((n, h, w, c), split, dy.device)
+    dres = empty_act((n, h, w, c), split, dy.device) if want_dres else None
     dgb = torch.empty((2, c), dtype=torch.float32, device=dy.device)
-    _lib.check(lib.semseg_bn_bwd_apply(_ptr(dy), dp, _ptr(y), yp, _ptr(x), xp, _ptr(mean_invstd), _ptr(gamma),
-                                       _ptr(scale_shift), _ptr(sums), float(count), n * h * w, c, int(bool(relu)), _ptr(dx), c,
-                                       _ptr(dres), c, _ptr(dgb), _stream()), "semseg_bn_bwd_apply")
+    _lib.check(lib.semseg_bn_bwd_apply(_ptr(dy), _lo(dy), dp, _ptr(y), _lo(y), yp, _ptr(x), _lo(x), xp,
+                                       _ptr(mean_invstd), _ptr(gamma), _ptr(scale_shift), _ptr(sums), float(count),
+                                       n * h * w, c, int(bool(relu)), _ptr(dx), _lo(dx), c, _ptr(dres), _lo(dres), c,
+                                       _ptr(dgb), _stream()), "semseg_bn_bwd_apply")
     return dx, dres, dgb
 
 
-def relu_bwd(dy, y):
-    lib = _lib.load()
-    n, h, w, c, dp = _nhwc_meta(dy)
-    yp = _nhwc_meta(y)[4]
-    dz = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
-    _lib.check(lib.semseg_relu_bwd(_ptr(dy), dp, _ptr(y), yp, _ptr(dz), c, n * h * w, c, _stream()),
-               "semseg_relu_bwd")
-    return dz
-
-
-def add_bf16(a, b, out=None):
+def add_act(a, b, out=None):
+    """a + b of two activations (either storage form; a split-aware add, unlike adding the planes)."""
     lib = _lib.load()
     n, h, w, c, ap = _nhwc_meta(a)
     bp = _nhwc_meta(b)[4]
     if out is None:
-        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=a.device)
+        out = empty_act((n, h, w, c), is_split(a), a.device)
     op = _nhwc_meta(out)[4]
-    _lib.check(lib.semseg_add_bf16(_ptr(a), ap, _ptr(b), bp, _ptr(out), op, n * h * w, c, _stream()),
-               "semseg_add_bf16")
+    _same_form(a, b, out)
+    _lib.check(lib.semseg_add_act(_ptr(a), _lo(a), ap, _ptr(b), _lo(b), bp, _ptr(out), _lo(out), op, n * h * w, c,
+                                  _stream()), "semseg_add_act")
+    return out
+
+
+def scale_nc(x, scale):
+    """x[n, :, :, c] * scale[n, c] (scale fp32 [N, C]): Dropout2d's per-(image, channel) factor."""
+    lib = _lib.load()
+    n, h, w, c, xp = _nhwc_meta(x)
+    assert scale.dtype == torch.float32 and scale.is_contiguous() and scale.numel() == n * c
+    out = empty_act((n, h, w, c), is_split(x), x.device)
+    _lib.check(lib.semseg_scale_nc(_ptr(x), _lo(x), xp, _ptr(scale), _ptr(out), _lo(out), c, n, h * w, c, _stream()),
+               "semseg_scale_nc")
+    return out
+
+
+def f32_to_act(x, split, pad_to=8):
+    """fp32 NHWC [N,H,W,C] (channel-contiguous, any pixel pitch) -> activation [N,H,W,Cp], Cp = C rounded up to
+    `pad_to`, padding zero filled."""
+    _require_cuda(x)
+    lib = _lib.load()
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.stride(-1) == 1
+    n, h, w, c = x.shape
+    sn, sh, sw, _ = x.stride()
+    assert sh == sw * w and sn == sh * h
+    cp = round_up(c, pad_to)
+    out = empty_act((n, h, w, cp), split, x.device)
+    _lib.check(lib.semseg_f32_to_act(_ptr(x), sw, _ptr(out), _lo(out), cp, n * h * w, c, cp, _stream()),
+               "semseg_f32_to_act")
+    return out
+
+
+def act_to_f32(x):
+    """activation -> fp32 NHWC [N,H,W,C]."""
+    lib = _lib.load()
+    n, h, w, c, p = _nhwc_meta(x)
+    out = torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
+    _lib.check(lib.semseg_act_to_f32(_ptr(x), _lo(x), p, _ptr(out), c, n * h * w, c, _stream()), "semseg_act_to_f32")
     return out
 
 
@@ -498,10 +619,12 @@ def upsample_ce_bwd(logits, target, ignore_index, lse, info, grad_out):
 
 # ------------------------------------------------------------------------------------------------ pyramid pooling
 def _bin_args(bins, tensors):
+    """(bins[], hi pointers[], lo pointers[] or NULL, nb)"""
     nb = len(bins)
     barr = (ctypes.c_int * nb)(*bins)
     parr = (ctypes.c_void_p * nb)(*[t.data_ptr() for t in tensors])
-    return barr, parr, nb
+    larr = (ctypes.c_void_p * nb)(*[_lo_int(t) for t in tensors]) if is_split(tensors[0]) else None
+    return barr, parr, larr, nb
 
 
 def ppm_pool(x, bins):
@@ -509,9 +632,9 @@ def ppm_pool(x, bins):
     _require_cuda(x)
     lib = _lib.load()
     n, h, w, c, p = _nhwc_meta(x)
-    outs = [torch.empty((n, b, b, c), dtype=torch.bfloat16, device=x.device) for b in bins]
-    barr, parr, nb = _bin_args(bins, outs)
-    _lib.check(lib.semseg_ppm_pool(_ptr(x), p, n, h, w, c, barr, parr, nb, _stream()), "semseg_ppm_pool")
+    outs = [empty_act((n, b, b, c), is_split(x), x.device) for b in bins]
+    barr, parr, larr, nb = _bin_args(bins, outs)
+    _lib.check(lib.semseg_ppm_pool(_ptr(x), _lo(x), p, n, h, w, c, barr, parr, larr, nb, _stream()), "semseg_ppm_pool")
     return outs
 
 
@@ -519,11 +642,12 @@ def ppm_pool_bwd(dpooled, bins, n, h, w, c, add=None):
     """dx of ppm_pool; `add` (NHWC bf16, possibly a channel slice of a wider tensor) is summed in."""
     lib = _lib.load()
     dpooled = [d.contiguous() for d in dpooled]
-    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dpooled[0].device)
-    barr, parr, nb = _bin_args(bins, dpooled)
+    dx = empty_act((n, h, w, c), is_split(dpooled[0]), dpooled[0].device)
+    barr, parr, larr, nb = _bin_args(bins, dpooled)
     ap = _nhwc_meta(add)[4] if add is not None else 0
-    _lib.check(lib.semseg_ppm_pool_bwd(parr, barr, nb, n, h, w, c, _ptr(dx), c, _ptr(add), ap, _stream()),
-               "semseg_ppm_pool_bwd")
+    _same_form(dx, add)
+    _lib.check(lib.semseg_ppm_pool_bwd(parr, larr, barr, nb, n, h, w, c, _ptr(dx), _lo(dx), c, _ptr(add), _lo(add), ap,
+                                       _stream()), "semseg_ppm_pool_bwd")
     return dx
 
 
@@ -533,20 +657,21 @@ def ppm_upsample_concat(x, feats, bins):
     n, h, w, c, p = _nhwc_meta(x)
     feats = [f.contiguous() for f in feats]
     cr = feats[0].shape[-1]
-    out = torch.empty((n, h, w, c + len(bins) * cr), dtype=torch.bfloat16, device=x.device)
-    barr, parr, nb = _bin_args(bins, feats)
-    _lib.check(lib.semseg_ppm_upsample_concat(_ptr(x), p, parr, barr, nb, n, h, w, c, cr, _ptr(out),
-                                              out.shape[-1], _stream()), "semseg_ppm_upsample_concat")
+    out = empty_act((n, h, w, c + len(bins) * cr), is_split(x), x.device)
+    barr, parr, larr, nb = _bin_args(bins, feats)
+    _same_form(x, feats[0])
+    _lib.check(lib.semseg_ppm_upsample_concat(_ptr(x), _lo(x), p, parr, larr, barr, nb, n, h, w, c, cr, _ptr(out),
+                                              _lo(out), out.shape[-1], _stream()), "semseg_ppm_upsample_concat")
     return out
 
 
 def ppm_upsample_bwd(dout, c_off, bins, cr):
     lib = _lib.load()
     n, h, w, ct, p = _nhwc_meta(dout)
-    dfeats = [torch.empty((n, b, b, cr), dtype=torch.bfloat16, device=dout.device) for b in bins]
-    barr, parr, nb = _bin_args(bins, dfeats)
-    _lib.check(lib.semseg_ppm_upsample_bwd(_ptr(dout), p, c_off, parr, barr, nb, n, h, w, cr, _stream()),
-               "semseg_ppm_upsample_bwd")
+    dfeats = [empty_act((n, b, b, cr), is_split(dout), dout.device) for b in bins]
+    barr, parr, larr, nb = _bin_args(bins, dfeats)
+    _lib.check(lib.semseg_ppm_upsample_bwd(_ptr(dout), _lo(dout), p, c_off, parr, larr, barr, nb, n, h, w, cr,
+                                           _stream()), "semseg_ppm_upsample_bwd")
     return dfeats
 
 
@@ -558,9 +683,9 @@ def maxpool3x3s2_fwd(x, want_argcode=True):
     n, h, w, c, p = _nhwc_meta(x)
     assert p == c, "maxpool expects a dense NHWC tensor"
     shape = (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c)
-    y = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    y = empty_act(shape, is_split(x), x.device)
     code = torch.empty(shape, dtype=torch.uint8, device=x.device) if want_argcode else None
-    _lib.check(lib.semseg_maxpool3x3s2_fwd(_ptr(x), _ptr(y), _ptr(code), n, h, w, c, _stream()),
+    _lib.check(lib.semseg_maxpool3x3s2_fwd(_ptr(x), _lo(x), _ptr(y), _lo(y), _ptr(code), n, h, w, c, _stream()),
                "semseg_maxpool3x3s2_fwd")
     return y, code
 
@@ -569,9 +694,9 @@ def maxpool3x3s2_bwd(argcode, dy, in_shape):
     lib = _lib.load()
     n, h, w, c = in_shape
     dy = dy.contiguous()
-    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
-    _lib.check(lib.semseg_maxpool3x3s2_bwd(_ptr(argcode), _ptr(dy), _ptr(dx), n, h, w, c, _stream()),
-               "semseg_maxpool3x3s2_bwd")
+    dx = empty_act((n, h, w, c), is_split(dy), dy.device)
+    _lib.check(lib.semseg_maxpool3x3s2_bwd(_ptr(argcode), _ptr(dy), _lo(dy), _ptr(dx), _lo(dx), n, h, w, c,
+                                           _stream()), "semseg_maxpool3x3s2_bwd")
     return dx
 
 
@@ -601,7 +726,9 @@ def bn_bwd_reduce_p2p(dy, y, x, mean_invstd, relu, scale_shift, px):
     ws, nf = bn_workspace(m, c, dy.device)
     out = torch.empty((2, 2, c), dtype=torch.float32, device=dy.device)
     slot, seq = px.next()
-    _lib.check(lib.semseg_bn_bwd_reduce_p2p(_ptr(dy), dp, _ptr(y), yp, _ptr(x), xp, _ptr(mean_invstd),
+    _same_form(dy, y, x)
+    _lib.check(lib.semseg_bn_bwd_reduce_p2p(_ptr(dy), _lo(dy), dp, _ptr(y), _lo(y), yp, _ptr(x), _lo(x), xp,
+                                            _ptr(mean_invstd),
                                             _ptr(scale_shift), m, c, int(bool(relu)), _ptr(ws), nf, _ptr(out[0]),
                                             _ptr(out[1]), px.data_ptrs, px.flag_ptrs, _ptr(px.counter), px.world,
                                             px.rank, slot,

@@ -52,13 +52,21 @@ def get_exchange(pg):
         return None
     key = id(pg)
     if key not in _exchanges:
+        ex, why = None, ""
         try:
-            _exchanges[key] = PeerExchange(pg)
+            ex = PeerExchange(pg)
         except Exception as e:      # noqa: BLE001 - symmetric memory unsupported here: use NCCL
+            why = str(e).splitlines()[0][:160] if str(e) else type(e).__name__
+        # every rank must take the same path: the peer kernels and the NCCL collectives cannot be mixed
+        okf = torch.tensor([1 if ex is not None else 0], dtype=torch.int32,
+                           device=torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN, group=pg)
+        if int(okf.item()) == 0:
             if dist.get_rank(pg) == 0:
-                print("semseg_b200: NVLink peer exchange unavailable (%s); SyncBN statistics go through NCCL" %
-                      str(e).splitlines()[0][:160])
-            _exchanges[key] = None
+                print("semseg_b200: NVLink peer exchange unavailable on at least one rank (%s); SyncBN statistics go "
+                      "through NCCL on all ranks" % (why or "a peer failed"))
+            ex = None
+        _exchanges[key] = ex
     return _exchanges[key]
 
 

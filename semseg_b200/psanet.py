@@ -17,6 +17,11 @@ from .pspnet import head_forward_nhwc, upsample_logits
 
 
 def _interp_nhwc(x, size):
+    """bilinear (align_corners=True) resize of an NHWC activation (model/psanet.py:61,97): fp32 arithmetic for split
+    activations, bf16 for plain ones."""
+    if ops.is_split(x):
+        y = F.interpolate(SF.act_to_f32(x).permute(0, 3, 1, 2), size=size, mode='bilinear', align_corners=True)
+        return SF.f32_to_act(y.permute(0, 2, 3, 1).contiguous(), True)
     y = F.interpolate(x.permute(0, 3, 1, 2), size=size, mode='bilinear', align_corners=True)
     return y.permute(0, 2, 3, 1).contiguous()
 
@@ -69,11 +74,13 @@ class PSA(nn.Module):
     def _branch(self, x, reduce, attention, mask_type):
         """x NHWC bf16 [n,H,W,C] -> aggregated features NHWC bf16 [n,h,w,mid] at the shrunk resolution."""
         t = SF.conv_bn_act(x, reduce[0], reduce[1], relu=True)
-        n, h, w, c = t.shape
+        split = ops.is_split(t)
+        n, h, w, c = t.shape[-4:]
         if self.shrink_factor != 1:
             h = (h - 1) // self.shrink_factor + 1
             w = (w - 1) // self.shrink_factor + 1
             t = _interp_nhwc(t, (h, w))
+        t, t_agg = SF.fork(t, 2)                              # t feeds the attention convs and the aggregation
         a = SF.conv_bn_act(t, attention[0], attention[1], relu=True)
         y = SF.conv_bias_f32(a, attention[3])                 # fp32 NHWC [n,h,w,mask_h*mask_w]
         y = y.permute(0, 3, 1, 2).contiguous()                # NCHW fp32, the layout psa_mask is defined on
@@ -85,28 +92,29 @@ class PSA(nn.Module):
         if self.psa_softmax:
             y = F.softmax(y, dim=1)
         # reference: bmm(x[n,c,hw], y[n,hw,hw]) -> [n,c,hw]; in NHWC that is y^T @ x[n,hw,c]
-        agg = torch.bmm(y.view(n, h * w, h * w).transpose(1, 2), t.reshape(n, h * w, c).float())
-        agg = agg * (1.0 / self.normalization_factor)
-        return agg.to(torch.bfloat16).view(n, h, w, c), (h, w)
+        tf = SF.act_to_f32(t_agg) if split else t_agg.float()
+        agg = torch.bmm(y.view(n, h * w, h * w).transpose(1, 2), tf.reshape(n, h * w, c))
+        agg = (agg * (1.0 / self.normalization_factor)).view(n, h, w, c)
+        return (SF.f32_to_act(agg, True) if split else agg.to(torch.bfloat16)), (h, w)
 
     def forward_nhwc(self, x):
-        out = x
         if self.psa_type in [0, 1]:
-            t, (h, w) = self._branch(x, self.reduce, self.attention, self.psa_type)
+            out, x1 = SF.fork(x, 2)
+            t, (h, w) = self._branch(x1, self.reduce, self.attention, self.psa_type)
         else:
-            t_col, (h, w) = self._branch(x, self.reduce, self.attention, 0)
-            t_dis, _ = self._branch(x, self.reduce_p, self.attention_p, 1)
-            t = torch.cat([t_col, t_dis], 3)
+            out, x1, x2 = SF.fork(x, 3)
+            t_col, (h, w) = self._branch(x1, self.reduce, self.attention, 0)
+            t_dis, _ = self._branch(x2, self.reduce_p, self.attention_p, 1)
+            t = torch.cat([t_col, t_dis], -1)
         t = SF.conv_bn_act(t, self.proj[0], self.proj[1], relu=True)
         if self.shrink_factor != 1:
             h = (h - 1) * self.shrink_factor + 1
             w = (w - 1) * self.shrink_factor + 1
             t = _interp_nhwc(t, (h, w))
-        return torch.cat((out, t), 3)
+        return torch.cat((out, t), -1)
 
     def forward(self, x):
-        y = self.forward_nhwc(SF.to_nhwc_bf16(x))
-        return y.permute(0, 3, 1, 2).float()
+        return SF.to_nchw_f32(self.forward_nhwc(SF.to_nhwc_bf16(x)))
 
 
 class PSANet(nn.Module):
@@ -176,13 +184,16 @@ class PSANet(nn.Module):
         t = self.layer1.forward_nhwc(t)
         t = self.layer2.forward_nhwc(t)
         t_tmp = self.layer3.forward_nhwc(t)
+        t_aux = None
+        if self.training:       # layer3's output feeds layer4 and the aux head: explicit fan-out (native gradient add)
+            t_tmp, t_aux = SF.fork(t_tmp, 2)
         t = self.layer4.forward_nhwc(t_tmp)
         if self.use_psa:
             t = self.psa.forward_nhwc(t)
         logits = head_forward_nhwc(self.cls, t)
 
         if self.training:
-            aux_logits = head_forward_nhwc(self.aux, t_tmp)
+            aux_logits = head_forward_nhwc(self.aux, t_aux)
             if SF.fused_tail_supported(self.criterion, logits, y, self.zoom_factor):
                 # upsample + cross-entropy + argmax fused: [N, classes, H, W] never exists (model/pspnet.py:94-103)
                 main_loss, pred = SF.upsample_ce(logits, y, self.criterion.ignore_index)

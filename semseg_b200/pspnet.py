@@ -38,8 +38,7 @@ class PPM(nn.Module):
         return SF.ppm_upsample_concat(x, feats, bins, link)      # one launch: upsample x4 + concat, written in place
 
     def forward(self, x):
-        y = self.forward_nhwc(SF.to_nhwc_bf16(x))
-        return y.permute(0, 3, 1, 2).float()
+        return SF.to_nchw_f32(self.forward_nhwc(SF.to_nhwc_bf16(x)))
 
 
 def head_forward_nhwc(head, t):
@@ -123,13 +122,16 @@ class PSPNet(nn.Module):
         t = self.layer1.forward_nhwc(t)
         t = self.layer2.forward_nhwc(t)
         t_tmp = self.layer3.forward_nhwc(t)
+        t_aux = None
+        if self.training:       # layer3's output feeds layer4 and the aux head: explicit fan-out (native gradient add)
+            t_tmp, t_aux = SF.fork(t_tmp, 2)
         t = self.layer4.forward_nhwc(t_tmp)
         if self.use_ppm:
             t = self.ppm.forward_nhwc(t)
         logits = head_forward_nhwc(self.cls, t)
 
         if self.training:
-            aux_logits = head_forward_nhwc(self.aux, t_tmp)
+            aux_logits = head_forward_nhwc(self.aux, t_aux)
             if SF.fused_tail_supported(self.criterion, logits, y, self.zoom_factor):
                 # upsample + cross-entropy + argmax fused: [N, classes, H, W] never exists (model/pspnet.py:94-103)
                 main_loss, pred = SF.upsample_ce(logits, y, self.criterion.ignore_index)

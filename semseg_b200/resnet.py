@@ -33,9 +33,7 @@ class NHWCSequential(nn.Sequential):
 
     def forward(self, x):
         # standalone use with an fp32 NCHW tensor (the reference's calling convention)
-        from . import ops
-        y = self.forward_nhwc(SF.to_nhwc_bf16(x))
-        return ops.nhwc_bf16_to_nchw(y) if not torch.is_grad_enabled() else y.permute(0, 3, 1, 2).float()
+        return SF.to_nchw_f32(self.forward_nhwc(SF.to_nhwc_bf16(x)))
 
 
 class Bottleneck(nn.Module):
@@ -58,9 +56,7 @@ class Bottleneck(nn.Module):
         return SF.bottleneck(x, self)
 
     def forward(self, x):
-        from . import ops
-        y = self.forward_nhwc(SF.to_nhwc_bf16(x))
-        return ops.nhwc_bf16_to_nchw(y) if not torch.is_grad_enabled() else y.permute(0, 3, 1, 2).float()
+        return SF.to_nchw_f32(self.forward_nhwc(SF.to_nhwc_bf16(x)))
 
 
 class Stem(NHWCSequential):
@@ -126,7 +122,7 @@ class ResNet(nn.Module):
         y = self.stem().forward_nhwc(SF.to_nhwc_bf16(x))
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             y = layer.forward_nhwc(y)
-        y = y.permute(0, 3, 1, 2).float()
+        y = SF.to_nchw_f32(y)
         y = self.avgpool(y)
         return self.fc(y.view(y.size(0), -1))
 

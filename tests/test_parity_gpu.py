@@ -328,7 +328,7 @@ def test_ppm_module_gradient_fan_in_vs_torch():
     import copy
     from semseg_b200.pspnet import PPM
     torch.manual_seed(3)
-    n, h, w, c, cr, bins = 6, 24, 24, 64, 16, (1, 2, 3, 6)
+    n, h, w, c, cr, bins = 6, 24, 24, 64, 64, (1, 2, 3, 6)
     ppm = PPM(c, cr, bins).cuda().train()
     ref = copy.deepcopy(ppm).float()
     g = torch.Generator(device="cuda").manual_seed(1)
