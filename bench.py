@@ -305,13 +305,19 @@ def run_b200_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(3, args.warmup)):
+    from semseg_b200 import graphs
+    inner = model.module if world > 1 else model
+    n_warm = max(3, args.warmup) + (graphs.WARMUP_CALLS + 1 if graphs.enabled() else 0)   # eager warm-up + graph capture
+    for _ in range(n_warm):
         step(x_dev, y_dev)
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = _lib.launch_count()
     ms_dev = timed(lambda: step(x_dev, y_dev), args.steps)
     launches = _lib.launch_count() - l0
+    graphed = graphs.launches_per_step(inner)
+    if graphed:                      # kernels replayed from the captured step graphs are not counted by the library
+        launches += graphed * args.steps
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     sampler.stop_flag = True
@@ -329,7 +335,7 @@ def run_b200_arm(args):
         psteps = max(1, min(args.steps, 5))
         try:
             with precision.mode("bf16x3"):
-                for _ in range(2):
+                for _ in range(2 + (graphs.WARMUP_CALLS + 1 if graphs.enabled() else 0)):
                     step(x_dev, y_dev)
                 ms_p = timed(lambda: step(x_dev, y_dev), psteps)
             parity = {"dtype": "bf16x3", "value": args.batch * world * psteps / (ms_p / 1e3), "unit": "images/sec",
@@ -395,6 +401,8 @@ def run_b200_arm(args):
                    "global_batch": args.batch * world, "parallelism": "dp%d" % world,
                    "l2": "inputs larger than L2: each step streams > 10 GB of activations through the 126 MB L2",
                    "optimizer": "SGD momentum 0.9 wd 1e-4, 8 param groups", "sync_bn": world > 1,
+                   "execution": ("forward and backward replayed as two CUDA graphs (%d kernels per step) behind one "
+                                 "autograd node" % graphed) if graphed else "eager launches",
                    "syncbn_exchange": __import__("semseg_b200.p2p", fromlist=["x"]).exchange_kind()},
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},

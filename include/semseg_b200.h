@@ -222,19 +222,22 @@ int semseg_bn_finalize_partials(const float* stats_partial, int rows, int C, con
 /* SyncBatchNorm exchange over NVLink peer memory instead of NCCL (one kernel per exchange). peer_bufs[world] /
  * peer_flags[world] are device pointers into every rank's symmetric (peer-mapped) allocation: a float buffer of
  * n_slots*slot_floats and a zero-initialised uint32 flag array [n_slots][world]; `counter` is a zeroed local uint32;
- * `slot` must be unique per exchange within a step and `seq` strictly increasing per step (same on every rank).
+ * `slot` must be unique per exchange within a step and the sequence number strictly increasing per step (same on every
+ * rank): it is `seq`, or — when seq_ptr is non-NULL — the uint32 read from that device address when the kernel runs (a
+ * device-resident step counter, so that a captured CUDA graph with baked-in slots can be replayed).
  *   finalize_p2p   : per-CTA conv partials -> exchange (mean, M2, n) -> cross-rank merge in rank order -> finalise.
  *   bwd_reduce_p2p : local [sum dz, sum dz*xhat] -> sums_local; exchanged and added in rank order -> sums_total. */
 int semseg_bn_finalize_p2p(const float* stats_partial, int rows, int C, const float* gamma, const float* beta,
                            float eps, float momentum, float* running_mean, float* running_var, float* mean_invstd,
                            float* scale_shift, void* const* peer_bufs, void* const* peer_flags, void* counter,
-                           int world, int rank, int slot, int slot_floats, unsigned seq, void* stream);
+                           int world, int rank, int slot, int slot_floats, unsigned seq, const void* seq_ptr,
+                           void* stream);
 int semseg_bn_bwd_reduce_p2p(const void* dy, const void* dy_lo, int dy_pitch, const void* y, const void* y_lo,
                              int y_pitch, const void* x, const void* x_lo, int x_pitch, const float* mean_invstd,
                              const float* scale_shift, int M, int C, int relu, float* workspace,
                              long long workspace_floats, float* sums_local, float* sums_total,
                              void* const* peer_bufs, void* const* peer_flags, void* counter, int world, int rank,
-                             int slot, int slot_floats, unsigned seq, void* stream);
+                             int slot, int slot_floats, unsigned seq, const void* seq_ptr, void* stream);
 /* Eval-mode folding: scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
 int semseg_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, int C, float* scale_shift, void* stream);

@@ -43,6 +43,31 @@ def build_ref(verbose=False):
     raise RuntimeError("reference extension did not produce a .so in %s" % ref_dir)
 
 
+def build_ref_gpu(verbose=False):
+    """The reference's own CUDA extension (lib/psa/src/gpu/{operator.cpp,psamask_cuda.cu} — "the kernel the rewrite must
+    beat") cross-compiled for sm_100 where the sources lie, into oracle/_ref/psamask_ref_gpu*.so. Used
+    only by tools/bench_psamask.py (a same-box timing of stock vs rewritten kernel). None when /root/reference is absent."""
+    gpu_dir = os.path.join(REFERENCE, "lib", "psa", "src", "gpu")
+    ref_dir = os.path.join(HERE, "_ref")
+
+    def found():
+        if os.path.isdir(ref_dir):
+            for f in os.listdir(ref_dir):
+                if f.startswith("psamask_ref_gpu") and f.endswith(".so"):
+                    return os.path.join(ref_dir, f)
+        return None
+    if found() or not os.path.isdir(gpu_dir):
+        return found()
+    os.makedirs(ref_dir, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    from torch.utils.cpp_extension import load
+    load(name="psamask_ref_gpu",
+         sources=[os.path.join(gpu_dir, "operator.cpp"), os.path.join(gpu_dir, "psamask_cuda.cu")],
+         build_directory=ref_dir, verbose=verbose, is_python_module=False)
+    return found()
+
+
 if __name__ == "__main__":
     print(build_oracle())
     print(build_ref(verbose="-v" in sys.argv))
+    print(build_ref_gpu(verbose="-v" in sys.argv))

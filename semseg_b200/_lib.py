@@ -104,10 +104,10 @@ SIGNATURES = {
     "semseg_bn_finalize": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "semseg_bn_finalize_partials": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "semseg_bn_finalize_p2p": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                       c_vp, c_int, c_int, c_int, c_int, ctypes.c_uint, c_vp]),
+                                       c_vp, c_int, c_int, c_int, c_int, ctypes.c_uint, c_vp, c_vp]),
     "semseg_bn_bwd_reduce_p2p": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int,
                                          c_int, c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int,
-                                         c_int, ctypes.c_uint, c_vp]),
+                                         c_int, ctypes.c_uint, c_vp, c_vp]),
     "semseg_bn_fold_eval": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_vp, c_vp]),
     "semseg_bn_apply": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                 c_vp]),

@@ -729,7 +729,9 @@ struct PeerArgs {
   unsigned* flags[8];   // peer-mapped flag arrays [slots][world]
   unsigned* counter;    // local block-arrival counter (self-resetting)
   int world, rank, slot, slot_floats;
-  unsigned seq;         // strictly increasing per training step
+  unsigned seq;         // sequence number of this exchange: the value of *seq_ptr when seq_ptr is given, else `seq`
+  const unsigned* seq_ptr;  // device-resident step counter (lets a captured CUDA graph be replayed: the slot is baked
+                            // into the graph, the sequence number is read at run time)
   long long timeout_ticks;
 };
 
@@ -759,6 +761,7 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
 // channels (a few thousand values, over NVLink).
 __device__ __forceinline__ bool peer_publish_and_wait(const PeerArgs& pa) {
   __shared__ int s_last;
+  const unsigned seq = pa.seq_ptr ? *pa.seq_ptr : pa.seq;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();                       // my block's stores to buf[rank] are visible system-wide ...
@@ -770,15 +773,15 @@ __device__ __forceinline__ bool peer_publish_and_wait(const PeerArgs& pa) {
   if (threadIdx.x == 0) {
     *pa.counter = 0u;
     __threadfence_system();
-    for (int p = 0; p < pa.world; ++p) st_release_sys(pa.flags[p] + pa.slot * pa.world + pa.rank, pa.seq);
+    for (int p = 0; p < pa.world; ++p) st_release_sys(pa.flags[p] + pa.slot * pa.world + pa.rank, seq);
   }
   if (threadIdx.x < pa.world) {
     const unsigned* f = pa.flags[pa.rank] + pa.slot * pa.world + threadIdx.x;
     const long long t0 = clock64();
-    while (ld_acquire_sys(f) != pa.seq) {
+    while (ld_acquire_sys(f) != seq) {
       if (clock64() - t0 > pa.timeout_ticks) {  // a peer that never arrives must not hang the GPU forever
         printf("semseg_b200: SyncBN peer exchange timed out (rank %d waiting for rank %d, slot %d, seq %u)\n", pa.rank,
-               static_cast<int>(threadIdx.x), pa.slot, pa.seq);
+               static_cast<int>(threadIdx.x), pa.slot, seq);
         __trap();
       }
     }
@@ -1151,7 +1154,7 @@ extern "C" int semseg_act_to_f32(const void* in, const void* in_lo, int in_pitch
 }
 
 static int fill_peer_args(sb::PeerArgs* pa, void* const* peer_bufs, void* const* peer_flags, void* counter, int world,
-                          int rank, int slot, int slot_floats, unsigned seq, int need_floats) {
+                          int rank, int slot, int slot_floats, unsigned seq, const void* seq_ptr, int need_floats) {
   SB_CHECK_ARG(peer_bufs && peer_flags && counter, "p2p: null peer tables");
   SB_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "p2p: world %d rank %d unsupported", world, rank);
   SB_CHECK_ARG(slot >= 0 && need_floats <= slot_floats, "p2p: slot too small (%d > %d floats)", need_floats,
@@ -1167,6 +1170,7 @@ static int fill_peer_args(sb::PeerArgs* pa, void* const* peer_bufs, void* const*
   pa->slot = slot;
   pa->slot_floats = slot_floats;
   pa->seq = seq;
+  pa->seq_ptr = static_cast<const unsigned*>(seq_ptr);
   static long long ticks = 0;
   if (ticks == 0) {
     const char* e = getenv("SEMSEG_B200_P2P_TIMEOUT_S");
@@ -1182,11 +1186,12 @@ extern "C" int semseg_bn_finalize_p2p(const float* stats_partial, int rows, int 
                                       const float* beta, float eps, float momentum, float* running_mean,
                                       float* running_var, float* mean_invstd, float* scale_shift,
                                       void* const* peer_bufs, void* const* peer_flags, void* counter, int world,
-                                      int rank, int slot, int slot_floats, unsigned seq, void* stream_) {
+                                      int rank, int slot, int slot_floats, unsigned seq, const void* seq_ptr,
+                                      void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(stats_partial && mean_invstd && scale_shift && rows > 0 && C > 0, "bn_finalize_p2p: bad args");
   sb::PeerArgs pa;
-  int r = fill_peer_args(&pa, peer_bufs, peer_flags, counter, world, rank, slot, slot_floats, seq, 3 * C);
+  int r = fill_peer_args(&pa, peer_bufs, peer_flags, counter, world, rank, slot, slot_floats, seq, seq_ptr, 3 * C);
   if (r) return r;
   switch (stats_group_channels(C)) {
     case 8: bn_finalize_p2p_kernel<8><<<cdiv(C, 8), 1024, 0, stream>>>(stats_partial, rows, C, gamma, beta, eps, momentum, running_mean, running_var, mean_invstd, scale_shift, pa); break;
@@ -1203,7 +1208,7 @@ extern "C" int semseg_bn_bwd_reduce_p2p(const void* dy, const void* dy_lo, int d
                                         float* workspace, long long workspace_floats, float* sums_local,
                                         float* sums_total, void* const* peer_bufs, void* const* peer_flags,
                                         void* counter, int world, int rank, int slot, int slot_floats, unsigned seq,
-                                        void* stream_) {
+                                        const void* seq_ptr, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SB_CHECK_ARG(dy && x && mean_invstd && workspace && sums_local && sums_total && M > 0 && C > 0,
                "bn_bwd_reduce_p2p: bad args");
@@ -1212,7 +1217,7 @@ extern "C" int semseg_bn_bwd_reduce_p2p(const void* dy, const void* dy_lo, int d
                "bn_bwd_reduce_p2p: channels and pitches must be multiples of 8");
   SB_CHECK_ARG(workspace_floats >= semseg_bn_workspace_floats(M, C), "bn_bwd_reduce_p2p: workspace too small");
   sb::PeerArgs pa;
-  int r = fill_peer_args(&pa, peer_bufs, peer_flags, counter, world, rank, slot, slot_floats, seq, 2 * C);
+  int r = fill_peer_args(&pa, peer_bufs, peer_flags, counter, world, rank, slot, slot_floats, seq, seq_ptr, 2 * C);
   if (r) return r;
   r = launch_bwd_reduce(dy, dy_lo, dy_pitch, y, y_lo, y_pitch, x, x_lo, x_pitch, mean_invstd, scale_shift, M, C, relu,
                         workspace, stream);

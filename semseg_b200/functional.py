@@ -72,9 +72,10 @@ def _is_patch_conv(conv, x):
             and conv.in_channels <= 3 and conv.groups == 1 and x.shape[-1] >= 4)
 
 
-def prepack(model):
+def prepack(model, force=False):
     """Refresh the operand slabs of every native conv of `model` in one launch when its weights changed (call at the top
-    of a training forward). Convs keep working without it: `packed` falls back to the per-layer kernels."""
+    of a training forward; force=True while the step is being captured into a CUDA graph, so that the re-pack is part
+    of every replay). Convs keep working without it: `packed` falls back to the per-layer kernels."""
     convs = [m for m in model.modules() if isinstance(m, nn.Conv2d) and m.weight.is_cuda and
              m.weight.dtype == torch.float32 and m.weight.is_contiguous() and m.kernel_size[0] == m.kernel_size[1] and
              m.kernel_size[0] * m.kernel_size[1] <= ops.MAX_TAPS]
@@ -82,7 +83,7 @@ def prepack(model):
         return
     split = precision.split_enabled()
     keys = [(c.weight._version, c.weight.data_ptr(), True, split) for c in convs]
-    if all(c.__dict__.get("_sb_pack", (None,))[0] == k for c, k in zip(convs, keys)):
+    if not force and all(c.__dict__.get("_sb_pack", (None,))[0] == k for c, k in zip(convs, keys)):
         return                                            # nothing changed since the last pack
     plan = model.__dict__.get("_sb_pack_plan")
     weights = [c.weight.detach() for c in convs]
@@ -436,12 +437,17 @@ class _UpsampleCE(torch.autograd.Function):
         return ops.upsample_ce_bwd(logits, target, ctx.ignore_index, lse, info, grad_loss), None, None
 
 
-def fused_tail_supported(criterion, logits, target, zoom_factor):
-    """The fused kernel implements exactly nn.CrossEntropyLoss(ignore_index=k) with default options at zoom 8."""
-    return (type(criterion) is nn.CrossEntropyLoss and criterion.weight is None and criterion.reduction == 'mean'
+def fused_tail_supported(criterion, logits, target, zoom_factor, x_size=None):
+    """The fused kernel implements exactly nn.CrossEntropyLoss(ignore_index=k) with default options at zoom 8.
+    `logits` fp32 NHWC, or None with the NCHW input size `x_size` (decision before the network has run)."""
+    if not (type(criterion) is nn.CrossEntropyLoss and criterion.weight is None and criterion.reduction == 'mean'
             and getattr(criterion, 'label_smoothing', 0.0) == 0.0 and zoom_factor == 8 and target is not None
-            and target.dtype == torch.int64 and target.dim() == 3 and logits.shape[-1] <= 256
-            and target.shape[1] == 8 * (logits.shape[1] - 1) + 1 and target.shape[2] == 8 * (logits.shape[2] - 1) + 1)
+            and target.dtype == torch.int64 and target.dim() == 3):
+        return False
+    if logits is None:
+        return target.shape[1] == x_size[2] and target.shape[2] == x_size[3]
+    return (logits.shape[-1] <= 256 and target.shape[1] == 8 * (logits.shape[1] - 1) + 1
+            and target.shape[2] == 8 * (logits.shape[2] - 1) + 1)
 
 
 def upsample_ce(logits, target, ignore_index):

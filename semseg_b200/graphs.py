@@ -1,0 +1,157 @@
+"""CUDA-graph execution of a whole training step (forward + backward) behind the unchanged module API.
+
+A PSPNet50 step is ~700 kernel launches (PSPNet101: ~1300) enqueued from Python; at the reference's own per-GPU batch
+(2 images, tool/train.py:154) the GPU finishes a step several times faster than the host can enqueue it, and under
+DistributedDataParallel every host hiccup turns into a cross-rank wait inside the SyncBatchNorm exchanges. After a few
+eager steps with the same input shape, `model(x, y)` in training mode therefore captures
+
+    forward  : module input -> (argmax, main_loss, aux_loss)              [one graph]
+    backward : d(main_loss, aux_loss)/d(parameters) via torch.autograd.grad [one graph]
+
+into two CUDA graphs (the same kernels, in the same order, on the same stream) and replays them from ONE autograd node
+whose inputs are the module's parameters: `loss.backward()`, DDP's gradient hooks, `optimizer.step()` and checkpoints see
+exactly what they saw before. Captured along with the kernels: the one-launch weight re-pack, the BatchNorm
+running-statistics updates, the SyncBN peer exchanges (their slots are baked in, the sequence number is a device-resident
+step counter incremented inside the graph — csrc/bn.cu peer_publish_and_wait) and dropout's Philox state.
+
+Limits (same as torch.cuda.make_graphed_callables): a second training forward before the backward of the first one
+overwrites the first one's saved activations — gradient accumulation over several forwards needs SEMSEG_B200_GRAPH=0.
+The NCCL fallback of the SyncBN exchange and non-default criteria are not captured (such models simply stay eager).
+Set SEMSEG_B200_GRAPH=0 to disable; any capture failure also falls back to the eager path (same kernels) with a warning.
+"""
+import os
+import warnings
+
+import torch
+import torch.distributed as dist
+
+from . import precision
+
+WARMUP_CALLS = 3          # eager calls with an unchanged key before capturing
+_capturing = False
+
+
+def enabled():
+    return os.environ.get("SEMSEG_B200_GRAPH", "1") != "0"
+
+
+def capturing():
+    """True while a step is being captured: per-step device work that the eager path skips when nothing changed (weight
+    re-pack, step-counter increment) must be issued unconditionally so that it becomes part of the graph."""
+    return _capturing
+
+
+class _Step:
+    __slots__ = ("key", "calls", "failed", "fwd", "bwd", "x", "y", "pred", "main", "aux", "g_main", "g_aux", "grads",
+                 "params", "pool", "keep", "launches")
+
+    def __init__(self, key):
+        self.key, self.calls, self.failed, self.fwd = key, 0, False, None
+
+
+class _Replay(torch.autograd.Function):
+    """One autograd node for the whole step: forward replays the forward graph, backward replays the backward graph and
+    returns the parameter gradients (static tensors of the graph's memory pool)."""
+
+    @staticmethod
+    def forward(ctx, st, x, y, *params):
+        st.x.copy_(x, non_blocking=True)
+        st.y.copy_(y, non_blocking=True)
+        st.fwd.replay()
+        ctx.st = st
+        pred, main, aux = st.pred.detach(), st.main.detach(), st.aux.detach()
+        ctx.mark_non_differentiable(pred)
+        return pred, main, aux
+
+    @staticmethod
+    def backward(ctx, _g_pred, g_main, g_aux):
+        st = ctx.st
+        if g_main is None:
+            st.g_main.zero_()
+        else:
+            st.g_main.copy_(g_main)
+        if g_aux is None:
+            st.g_aux.zero_()
+        else:
+            st.g_aux.copy_(g_aux)
+        st.bwd.replay()
+        return (None, None, None) + tuple(g.detach() if g is not None else None for g in st.grads)
+
+
+def _sync_bn_ready(model):
+    """(ok, exchange): multi-rank SyncBatchNorm is only captured with the NVLink peer exchange (no NCCL call inside)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return True
+    if not any(isinstance(m, torch.nn.SyncBatchNorm) for m in model.modules()):
+        return True
+    from . import p2p
+    return p2p.get_exchange(dist.group.WORLD) is not None
+
+
+def _capture(model, impl, st, x, y):
+    global _capturing
+    from . import _lib
+    params = [p for p in model.parameters() if p.requires_grad]
+    st.params = params
+    st.x, st.y = torch.empty_like(x), torch.empty_like(y)
+    st.x.copy_(x)
+    st.y.copy_(y)
+    torch.cuda.synchronize()
+    st.pool = torch.cuda.graph_pool_handle()
+    st.fwd, st.bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    l0 = _lib.launch_count()
+    _capturing = True
+    try:
+        with torch.cuda.graph(st.fwd, pool=st.pool, capture_error_mode="thread_local"):
+            with torch.enable_grad():
+                st.pred, st.main, st.aux = impl(st.x, st.y)
+        st.g_main, st.g_aux = torch.ones_like(st.main), torch.ones_like(st.aux)
+        with torch.cuda.graph(st.bwd, pool=st.pool, capture_error_mode="thread_local"):
+            st.grads = torch.autograd.grad((st.main, st.aux), params, (st.g_main, st.g_aux), allow_unused=True)
+    finally:
+        _capturing = False
+    st.launches = _lib.launch_count() - l0          # native kernels per replayed step (forward + backward graphs)
+    # drop the autograd graph built during capture (its AccumulateGrad nodes are bound to the capture stream and would
+    # be kept alive by the loss tensors); the static outputs live on in the graphs' private memory pool
+    st.pred, st.main, st.aux = st.pred.detach(), st.main.detach(), st.aux.detach()
+    # the graphs reference the persistent weight slabs: keep their owner alive as long as the graphs
+    st.keep = model.__dict__.get("_sb_pack_plan")
+    torch.cuda.synchronize()
+
+
+def train_step(model, impl, x, y):
+    """Run `impl(x, y)` (the module's eager training forward, returning (pred, main_loss, aux_loss)) through the captured
+    graphs when possible; returns None when the caller should run the eager path itself."""
+    if not (enabled() and x.is_cuda and y is not None and torch.is_grad_enabled()):
+        return None
+    steps = model.__dict__.setdefault("_sb_graph_steps", {})
+    nparams = sum(1 for p in model.parameters() if p.requires_grad)
+    key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, x.device.index, precision.get_mode(), nparams,
+           dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1)
+    st = steps.get(key)
+    if st is None:
+        st = steps[key] = _Step(key)
+    if st.failed:
+        return None
+    if st.fwd is None:
+        st.calls += 1
+        if st.calls <= WARMUP_CALLS:
+            return None                       # eager warm-up (also creates the weight-pack plan, the peer exchange, ...)
+        if not _sync_bn_ready(model):
+            st.failed = True
+            return None
+        try:
+            _capture(model, impl, st, x, y)
+        except Exception as e:      # noqa: BLE001 - stay on the eager path (same kernels), say so once
+            st.failed, st.fwd = True, None
+            warnings.warn("semseg_b200: CUDA-graph capture of the training step failed (%s: %s); continuing eagerly" %
+                          (type(e).__name__, str(e).splitlines()[0][:200] if str(e) else ""))
+            torch.cuda.synchronize()
+            return None
+    return _Replay.apply(st, x, y, *st.params)
+
+
+def launches_per_step(model):
+    """Native kernel launches inside one replayed step of `model` (0 when no step has been captured)."""
+    steps = model.__dict__.get("_sb_graph_steps", {})
+    return max([getattr(s, "launches", 0) or 0 for s in steps.values() if s.fwd is not None] + [0])

@@ -10,8 +10,9 @@ from . import _lib
 from ._lib import ConvDesc, WgradDesc, EPI_RAW, EPI_AFFINE, EPI_F32, MAX_TAPS
 
 
-# bf16x3: K blocks (64-channel block x tap) one tensor-core accumulation chain may span (21 x 4 x 3 = 252 MMA steps)
-X3_MAX_KBLOCKS = 21
+# bf16x3: K blocks (64-channel block x tap) one tensor-core accumulation chain may span (8 x 4 x 3 = 96 MMA steps; the
+# truncating fp32 accumulation of tcgen05 loses ~2^-24 per step towards zero, tools/probe_accum.py)
+X3_MAX_KBLOCKS = 8
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 _cur_device = getattr(torch._C, "_cuda_getDevice", None)
@@ -712,7 +713,7 @@ def bn_finalize_p2p(stats_partial, gamma, beta, eps, momentum, running_mean, run
                                           float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(mi), _ptr(ss),
                                           px.data_ptrs, px.flag_ptrs, _ptr(px.counter), px.world, px.rank, slot,
                                           int(__import__("semseg_b200.p2p", fromlist=["x"]).SLOT_FLOATS), seq,
-                                          _stream()), "semseg_bn_finalize_p2p")
+                                          _ptr(px.step), _stream()), "semseg_bn_finalize_p2p")
     return mi, ss
 
 
@@ -733,5 +734,5 @@ def bn_bwd_reduce_p2p(dy, y, x, mean_invstd, relu, scale_shift, px):
                                             _ptr(out[1]), px.data_ptrs, px.flag_ptrs, _ptr(px.counter), px.world,
                                             px.rank, slot,
                                             int(__import__("semseg_b200.p2p", fromlist=["x"]).SLOT_FLOATS), seq,
-                                            _stream()), "semseg_bn_bwd_reduce_p2p")
+                                            _ptr(px.step), _stream()), "semseg_bn_bwd_reduce_p2p")
     return out[0], out[1]

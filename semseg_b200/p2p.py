@@ -34,16 +34,32 @@ class PeerExchange:
         self.flag_ptrs = (ctypes.c_void_p * self.world)(*ptrs)
         self.data_ptrs = (ctypes.c_void_p * self.world)(*[p + 4 * flag_words for p in ptrs])
         self.counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        # Device-resident step counter = the sequence number of every exchange of the current step. The kernels read it
+        # when they run, so a training step captured in a CUDA graph (slots baked in) can be replayed: the graph only
+        # has to contain the increment (begin_step) once per step.
+        self.step = torch.ones((1,), dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
         self.handle.barrier()           # every rank's flags are zero before the first exchange
         torch.cuda.synchronize()
         self.calls = 0
 
+    def begin_step(self, force=False):
+        """Start a new exchange epoch: slots are handed out from 0 again under a new sequence number. Called at the top
+        of every training forward (same point on every rank); a slot is reused only after at least one other exchange
+        of the same or the following step, which orders the reuse after every peer's reads of the old contents.
+        force=True (while a step is captured into a CUDA graph) issues the increment unconditionally."""
+        if self.calls or force:
+            self.step.add_(1)           # a (capturable) device-side increment
+            self.calls = 0
+
     def next(self):
-        """(slot, seq) of the next exchange: identical on every rank because all ranks run the same op sequence."""
+        """(slot, seq) of the next exchange: identical on every rank because all ranks run the same op sequence.
+        seq = 0 tells the kernel to take the sequence number from the device-resident step counter."""
+        if self.calls >= N_SLOTS:       # more exchanges than slots without a begin_step(): open a new epoch
+            self.begin_step()
         k = self.calls
         self.calls += 1
-        return k % N_SLOTS, k // N_SLOTS + 1
+        return k, 0
 
 
 def get_exchange(pg):
@@ -68,6 +84,15 @@ def get_exchange(pg):
             ex = None
         _exchanges[key] = ex
     return _exchanges[key]
+
+
+def begin_step(pg=None, force=False):
+    """Open a new exchange epoch on the (already created) peer exchange of `pg`; no-op without one."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    ex = _exchanges.get(id(pg if pg is not None else dist.group.WORLD))
+    if ex is not None:
+        ex.begin_step(force)
 
 
 def exchange_kind(pg=None):

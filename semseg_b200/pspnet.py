@@ -7,7 +7,9 @@ from torch import nn
 import torch.nn.functional as F
 
 from . import functional as SF
+from . import graphs
 from . import ops
+from . import p2p
 from . import resnet as models
 
 
@@ -112,11 +114,22 @@ class PSPNet(nn.Module):
     def forward(self, x, y=None):
         x_size = x.size()
         assert (x_size[2] - 1) % 8 == 0 and (x_size[3] - 1) % 8 == 0
+        if (self.training and torch.is_grad_enabled() and y is not None and
+                SF.fused_tail_supported(self.criterion, None, y, self.zoom_factor, x_size)):
+            # whole training step (forward and, later, backward) as two replayed CUDA graphs behind one autograd node
+            out = graphs.train_step(self, self._forward_impl, x, y)
+            if out is not None:
+                return out
+        return self._forward_impl(x, y)
+
+    def _forward_impl(self, x, y=None):
+        x_size = x.size()
         h = int((x_size[2] - 1) / 8 * self.zoom_factor + 1)
         w = int((x_size[3] - 1) / 8 * self.zoom_factor + 1)
 
         if self.training and torch.is_grad_enabled():
-            SF.prepack(self)      # all conv operand slabs refreshed in one launch after an optimizer step
+            SF.prepack(self, force=graphs.capturing())   # all conv operand slabs refreshed in one launch
+            p2p.begin_step(force=graphs.capturing())     # new SyncBN exchange epoch (device-resident step counter)
         t = SF.to_nhwc_bf16(x)
         t = self.layer0.forward_nhwc(t)
         t = self.layer1.forward_nhwc(t)

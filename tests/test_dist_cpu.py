@@ -63,15 +63,18 @@ def test_peer_exchange_slot_sequence_and_nccl_override(monkeypatch):
     class Fake(p2p.PeerExchange):
         def __init__(self):
             self.calls = 0
+            self.step = torch.ones((1,), dtype=torch.int32)      # the device-resident step counter (CPU stand-in)
     a, b = Fake(), Fake()
     seen = {}
-    for _ in range(3 * p2p.N_SLOTS + 5):
+    for k in range(3 * p2p.N_SLOTS + 5):
+        if k % 200 == 199:          # a training forward opens a new epoch on every rank at the same point
+            a.begin_step(), b.begin_step()
         sa, sb_ = a.next(), b.next()
-        assert sa == sb_
+        assert sa == sb_ and int(a.step) == int(b.step)
         slot, seq = sa
-        assert 0 <= slot < p2p.N_SLOTS and seq >= 1
-        assert seq > seen.get(slot, 0)
-        seen[slot] = seq
+        assert 0 <= slot < p2p.N_SLOTS and seq == 0     # seq 0: the kernel reads the step counter
+        assert int(a.step) > seen.get(slot, 0)          # a slot is only reused under a larger sequence number
+        seen[slot] = int(a.step)
     assert p2p.SLOT_FLOATS >= 3 * 2048          # widest BatchNorm on the path (layer4 / PSA proj: 2048 channels)
     monkeypatch.setenv("SEMSEG_B200_SYNCBN", "nccl")
     assert p2p.get_exchange(object()) is None

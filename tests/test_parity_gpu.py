@@ -236,6 +236,7 @@ def test_peer_exchange_kernels_world_of_one():
             self.flag_ptrs = (ctypes.c_void_p * 1)(self.buf.data_ptr())
             self.data_ptrs = (ctypes.c_void_p * 1)(self.buf.data_ptr() + 4 * flag_words)
             self.counter = torch.zeros((1,), dtype=torch.int32, device="cuda")
+            self.step = torch.ones((1,), dtype=torch.int32, device="cuda")
 
     px = LocalExchange()
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -365,7 +366,7 @@ def test_ppm_module_gradient_fan_in_vs_torch():
     assert torch.equal(dx_id, go_id[..., :c])
     _, dx = ours(go_full)
     _, dx_ref = theirs(go_full)
-    assert util.rel_l2(dx, dx_ref) < 1e-2
+    assert util.rel_l2(dx, dx_ref) < 5e-2        # identity part exact + pooled part at the bf16 tolerance above
 
 
 def test_maxpool_vs_torch_with_ties():
