@@ -57,6 +57,25 @@ int semseg_psamask_bwd(int psa_type, const float* dout, float* din, int N, int H
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused point-wise spatial attention (model/psanet.py:81-91: psa_mask -> softmax(dim=1) -> bmm): the
+ * [N, HW, HW] attention map never exists in HBM.
+ *   attn  fp32 NHWC [N, H*W, a_pitch] (a_pitch >= mH*mW): the attention logits as the 1x1 conv's F32 epilogue writes them
+ *   feat / out / dout  activations NHWC [N, H*W, C] (C = 512), plain bf16 or split (hi, lo)
+ *   stats fp32 [N, H*W, 2] = (max, 1/sum) of every target's softmax (written by mode 0, read by the backward calls)
+ * semseg_psa_attend  mode 0: out[t,:]   = scale * sum_s P[t,s] * feat[s,:]   (forward; P = softmax over sources s)
+ *                    mode 1: out[s,:]   = scale * sum_t P[t,s] * feat[t,:]   (feature gradient: pass dout as feat)
+ * semseg_psa_attend_bwd_attn: dattn (same shape as attn, every element written: zero where the mask window gives no
+ *   gradient) = P * (scale * dout . feat^T - rowsum(dout * out)) scattered back through the mask index map.
+ * psa_type 0 = collect, 1 = distribute (lib/psa/functions/psamask.py:9). */
+int semseg_psa_attend(int mode, int psa_type, const float* attn, int a_pitch, const void* feat, const void* feat_lo,
+                      int feat_pitch, float* stats, void* out, void* out_lo, int out_pitch, int N, int H, int W, int mH,
+                      int mW, int C, float scale, void* stream);
+int semseg_psa_attend_bwd_attn(int psa_type, const float* attn, int a_pitch, const float* stats, const void* feat,
+                               const void* feat_lo, int feat_pitch, const void* out, const void* out_lo, int out_pitch,
+                               const void* dout, const void* dout_lo, int dout_pitch, float* dattn, int N, int H, int W,
+                               int mH, int mW, int C, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).
  *
  * One descriptor drives fprop and dgrad (dgrad = fprop of dY with the transposed/flipped packed
@@ -305,6 +324,15 @@ int semseg_ppm_upsample_concat(const void* x, const void* x_lo, int x_pitch, voi
                                int out_pitch, void* stream);
 int semseg_ppm_upsample_bwd(const void* dout, const void* dout_lo, int dout_pitch, int c_off, void* const* dfeats,
                             void* const* dfeats_lo, const int* bins, int nb, int N, int H, int W, int Cr, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bilinear resize, align_corners=True, of an NHWC activation [N,Hi,Wi,C] -> [N,Ho,Wo,C] (F.interpolate at
+ * model/psanet.py:61,97) and its adjoint (dy [N,Ho,Wo,C] -> dx [N,Hi,Wi,C]; a deterministic gather, no atomics).
+ */
+int semseg_resize_bilinear_fwd(const void* x, const void* x_lo, int x_pitch, int N, int Hi, int Wi, int C, int Ho,
+                               int Wo, void* y, void* y_lo, int y_pitch, void* stream);
+int semseg_resize_bilinear_bwd(const void* dy, const void* dy_lo, int dy_pitch, int N, int Hi, int Wi, int C, int Ho,
+                               int Wo, void* dx, void* dx_lo, int dx_pitch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused logit upsample (bilinear, align_corners=True, x8) + cross-entropy (ignore_index, mean over valid

@@ -80,6 +80,10 @@ SIGNATURES = {
     "semseg_launch_count": (c_ll, []),
     "semseg_psamask_fwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "semseg_psamask_bwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "semseg_psa_attend": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int, c_f, c_vp]),
+    "semseg_psa_attend_bwd_attn": (c_int, [c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp,
+                                           c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f, c_vp]),
     "semseg_conv_stats_rows": (c_int, [c_int, c_int, c_int, c_int]),
     "semseg_conv_k_slices": (c_int, [c_int, c_int, c_int]),
     "semseg_conv_splitk_rows": (c_int, [c_int]),
@@ -128,6 +132,10 @@ SIGNATURES = {
                                            c_int, c_vp, c_vp, c_int, c_vp]),
     "semseg_ppm_upsample_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                                         c_vp]),
+    "semseg_resize_bilinear_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int,
+                                           c_vp]),
+    "semseg_resize_bilinear_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int,
+                                           c_vp]),
     "semseg_upsample_ce_workspace_floats": (c_ll, [c_int, c_int, c_int]),
     "semseg_upsample_ce_fwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp,
                                        c_vp, c_vp, c_vp, c_vp]),

@@ -15,118 +15,76 @@
 
 namespace sb {
 
-// Work decomposition: a block owns (n, h) and G consecutive target rows i (forward) or mask rows a (backward); one WARP
-// moves one row at a time with lane = position inside the row (W <= 32: the shipped 30x30 / 59x59 geometry; wider maps take
-// the strided loop), so there is no per-element index division, and every lane keeps kRowsInFlight independent row loads
-// in flight before the first shared-memory write (the kernel is latency-bound: rows are 120 bytes at a 3600-byte pitch).
-constexpr int kPsaThreads = 256;
-constexpr int kPsaWarps = kPsaThreads / 32;
-constexpr int kRowsInFlight = 6;
-constexpr int kPsaG = 2;
-
-// TYPE 0 = collect, 1 = distribute. grid = N * H * ceil(H / G) blocks (n, h, i-group).
+// TYPE 0 = collect, 1 = distribute. grid = N*H*H blocks (n, h, i).
 template <int TYPE>
-__global__ void __launch_bounds__(kPsaThreads) psamask_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                                  int N, int H, int W, int mH, int mW) {
-  extern __shared__ float S[];   // [G][mW][P]
+__global__ void __launch_bounds__(128) psamask_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                          int N, int H, int W, int mH, int mW) {
+  extern __shared__ float S[];
   const int hh = (mH - 1) / 2, hw = (mW - 1) / 2;
   const int P = TYPE == 0 ? ((W | 1) + 1) : (W | 1);
-  const int groups = (H + kPsaG - 1) / kPsaG;
-  const int ig = blockIdx.x % groups;
-  const int h = (blockIdx.x / groups) % H;
-  const int n = blockIdx.x / (groups * H);
-  const int i0 = ig * kPsaG;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x % H;
+  const int h = (blockIdx.x / H) % H;
+  const int n = blockIdx.x / (H * H);
+  const int a = i - h + hh;
+  const bool a_ok = a >= 0 && a < mH;
   const size_t HW = static_cast<size_t>(H) * W;
-  const float* src_n = in + static_cast<size_t>(n) * mH * mW * HW + static_cast<size_t>(h) * W;
-  const int rows_in = kPsaG * mW;
-  for (int w0 = 0; w0 < W; w0 += 32) {          // one pass for W <= 32
-    const int w = w0 + lane;
-    for (int r0 = warp * kRowsInFlight; r0 < rows_in; r0 += kPsaWarps * kRowsInFlight) {
-      float v[kRowsInFlight];
-      bool ok[kRowsInFlight];
-#pragma unroll
-      for (int u = 0; u < kRowsInFlight; ++u) {
-        const int r = r0 + u;
-        const int g = r / mW, b = r - g * mW;
-        const int i = i0 + g, a = i - h + hh, j = b + w - hw;
-        ok[u] = r < rows_in && i < H && a >= 0 && a < mH && w < W && j >= 0 && j < W;
-        v[u] = ok[u] ? src_n[(static_cast<size_t>(a) * mW + b) * HW + w] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < kRowsInFlight; ++u)
-        if (ok[u]) S[(r0 + u) * P + w] = v[u];
+  if (a_ok) {
+    const float* src = in + ((static_cast<size_t>(n) * mH * mW + static_cast<size_t>(a) * mW) * H + h) * W;
+    for (int idx = threadIdx.x; idx < mW * W; idx += blockDim.x) {
+      const int b = idx / W, w = idx - b * W;
+      const int j = b + w - hw;
+      if (j >= 0 && j < W) S[b * P + w] = src[static_cast<size_t>(b) * HW + w];
     }
   }
   __syncthreads();
-  const int rows_out = kPsaG * W;
-  for (int r = warp; r < rows_out; r += kPsaWarps) {
-    const int g = r / W, k = r - g * W;          // k = j (collect) or w (distribute)
-    const int i = i0 + g, a = i - h + hh;
-    if (i >= H) break;
-    const bool a_ok = a >= 0 && a < mH;
-    for (int c = lane; c < W; c += 32) {         // c = w (collect) or j (distribute)
-      const int j = TYPE == 0 ? k : c, w = TYPE == 0 ? c : k;
-      const int b = j - w + hw;
-      const float v = (a_ok && b >= 0 && b < mW) ? S[(g * mW + b) * P + w] : 0.f;
-      if (TYPE == 0)
-        out[((static_cast<size_t>(n) * HW + static_cast<size_t>(i) * W + j) * H + h) * W + w] = v;
-      else
-        out[((static_cast<size_t>(n) * HW + static_cast<size_t>(h) * W + w) * H + i) * W + j] = v;
+  for (int idx = threadIdx.x; idx < W * W; idx += blockDim.x) {
+    int j, w;
+    if (TYPE == 0) {
+      j = idx / W;
+      w = idx - j * W;
+    } else {
+      w = idx / W;
+      j = idx - w * W;
     }
+    const int b = j - w + hw;
+    const float v = (a_ok && b >= 0 && b < mW) ? S[b * P + w] : 0.f;
+    if (TYPE == 0)
+      out[((static_cast<size_t>(n) * HW + static_cast<size_t>(i) * W + j) * H + h) * W + w] = v;
+    else
+      out[((static_cast<size_t>(n) * HW + static_cast<size_t>(h) * W + w) * H + i) * W + j] = v;
   }
 }
 
-// grid = N * H * ceil(mH / G) blocks (n, h, a-group): writes the whole din slabs [mW][W] (zeros where nothing maps).
+// grid = N*H*mH blocks (n, h, a): writes the whole din slab [mW][W] (zeros where nothing maps).
 template <int TYPE>
-__global__ void __launch_bounds__(kPsaThreads) psamask_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din,
-                                                                  int N, int H, int W, int mH, int mW) {
-  extern __shared__ float S[];   // [G][W][P]
+__global__ void __launch_bounds__(128) psamask_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din,
+                                                          int N, int H, int W, int mH, int mW) {
+  extern __shared__ float S[];
   const int hh = (mH - 1) / 2, hw = (mW - 1) / 2;
   const int P = (W | 1) + 1;
-  const int groups = (mH + kPsaG - 1) / kPsaG;
-  const int ag = blockIdx.x % groups;
-  const int h = (blockIdx.x / groups) % H;
-  const int n = blockIdx.x / (groups * H);
-  const int a0 = ag * kPsaG;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a = blockIdx.x % mH;
+  const int h = (blockIdx.x / mH) % H;
+  const int n = blockIdx.x / (mH * H);
+  const int i = a + h - hh;
+  const bool i_ok = i >= 0 && i < H;
   const size_t HW = static_cast<size_t>(H) * W;
-  const int rows_in = kPsaG * W;
-  for (int c0 = 0; c0 < W; c0 += 32) {
-    const int c = c0 + lane;
-    for (int r0 = warp * kRowsInFlight; r0 < rows_in; r0 += kPsaWarps * kRowsInFlight) {
-      float v[kRowsInFlight];
-      bool ok[kRowsInFlight];
-#pragma unroll
-      for (int u = 0; u < kRowsInFlight; ++u) {
-        const int r = r0 + u;
-        const int g = r / W, k = r - g * W;       // k = j (collect) or w (distribute); c = the other one
-        const int a = a0 + g, i = a + h - hh;
-        ok[u] = r < rows_in && a < mH && i >= 0 && i < H && c < W;
-        size_t off = 0;
-        if (TYPE == 0) off = ((static_cast<size_t>(n) * HW + static_cast<size_t>(i) * W + k) * H + h) * W + c;
-        else off = ((static_cast<size_t>(n) * HW + static_cast<size_t>(h) * W + k) * H + i) * W + c;
-        v[u] = ok[u] ? dout[off] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < kRowsInFlight; ++u)
-        if (ok[u]) S[(r0 + u) * P + c] = v[u];
+  if (i_ok) {
+    for (int idx = threadIdx.x; idx < W * W; idx += blockDim.x) {
+      const int r = idx / W, c = idx - r * W;
+      if (TYPE == 0)  // r = j, c = w
+        S[r * P + c] = dout[((static_cast<size_t>(n) * HW + static_cast<size_t>(i) * W + r) * H + h) * W + c];
+      else  // r = w, c = j
+        S[r * P + c] = dout[((static_cast<size_t>(n) * HW + static_cast<size_t>(h) * W + r) * H + i) * W + c];
     }
   }
   __syncthreads();
-  const int rows_out = kPsaG * mW;
-  for (int r = warp; r < rows_out; r += kPsaWarps) {
-    const int g = r / mW, b = r - g * mW;
-    const int a = a0 + g, i = a + h - hh;
-    if (a >= mH) break;
-    const bool i_ok = i >= 0 && i < H;
-    float* dst = din + ((static_cast<size_t>(n) * mH * mW + static_cast<size_t>(a) * mW + b) * H + h) * W;
-    for (int w = lane; w < W; w += 32) {
-      const int j = b + w - hw;
-      float v = 0.f;
-      if (i_ok && j >= 0 && j < W) v = TYPE == 0 ? S[(g * W + j) * P + w] : S[(g * W + w) * P + j];
-      dst[w] = v;
-    }
+  float* dst = din + ((static_cast<size_t>(n) * mH * mW + static_cast<size_t>(a) * mW) * H + h) * W;
+  for (int idx = threadIdx.x; idx < mW * W; idx += blockDim.x) {
+    const int b = idx / W, w = idx - b * W;
+    const int j = b + w - hw;
+    float v = 0.f;
+    if (i_ok && j >= 0 && j < W) v = TYPE == 0 ? S[j * P + w] : S[w * P + j];
+    dst[static_cast<size_t>(b) * HW + w] = v;
   }
 }
 
@@ -147,17 +105,17 @@ extern "C" int semseg_psamask_fwd(int psa_type, const float* in, float* out, int
   int r = check_psa(psa_type, in, out, N, H, W, mH, mW);
   if (r) return r;
   const int P = (W | 1) + 1;
-  const size_t smem = static_cast<size_t>(kPsaG) * mW * P * sizeof(float);
+  const size_t smem = static_cast<size_t>(mW) * P * sizeof(float);
   SB_CHECK_ARG(smem <= 200 * 1024, "psamask: mask too large for shared memory");
-  const unsigned grid = static_cast<unsigned>(N) * H * ((H + kPsaG - 1) / kPsaG);
+  const unsigned grid = static_cast<unsigned>(N) * H * H;
   if (psa_type == 0) {
     if (smem > 48 * 1024)
       SB_CUDA(cudaFuncSetAttribute(psamask_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    psamask_fwd_kernel<0><<<grid, kPsaThreads, smem, stream>>>(in, out, N, H, W, mH, mW);
+    psamask_fwd_kernel<0><<<grid, 128, smem, stream>>>(in, out, N, H, W, mH, mW);
   } else {
     if (smem > 48 * 1024)
       SB_CUDA(cudaFuncSetAttribute(psamask_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    psamask_fwd_kernel<1><<<grid, kPsaThreads, smem, stream>>>(in, out, N, H, W, mH, mW);
+    psamask_fwd_kernel<1><<<grid, 128, smem, stream>>>(in, out, N, H, W, mH, mW);
   }
   SB_LAUNCHED();
   return SEMSEG_OK;
@@ -170,17 +128,17 @@ extern "C" int semseg_psamask_bwd(int psa_type, const float* dout, float* din, i
   int r = check_psa(psa_type, dout, din, N, H, W, mH, mW);
   if (r) return r;
   const int P = (W | 1) + 1;
-  const size_t smem = static_cast<size_t>(kPsaG) * W * P * sizeof(float);
+  const size_t smem = static_cast<size_t>(W) * P * sizeof(float);
   SB_CHECK_ARG(smem <= 200 * 1024, "psamask: feature map too large for shared memory");
-  const unsigned grid = static_cast<unsigned>(N) * H * ((mH + kPsaG - 1) / kPsaG);
+  const unsigned grid = static_cast<unsigned>(N) * H * mH;
   if (psa_type == 0) {
     if (smem > 48 * 1024)
       SB_CUDA(cudaFuncSetAttribute(psamask_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    psamask_bwd_kernel<0><<<grid, kPsaThreads, smem, stream>>>(dout, din, N, H, W, mH, mW);
+    psamask_bwd_kernel<0><<<grid, 128, smem, stream>>>(dout, din, N, H, W, mH, mW);
   } else {
     if (smem > 48 * 1024)
       SB_CUDA(cudaFuncSetAttribute(psamask_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    psamask_bwd_kernel<1><<<grid, kPsaThreads, smem, stream>>>(dout, din, N, H, W, mH, mW);
+    psamask_bwd_kernel<1><<<grid, 128, smem, stream>>>(dout, din, N, H, W, mH, mW);
   }
   SB_LAUNCHED();
   return SEMSEG_OK;

@@ -518,6 +518,61 @@ def ppm_link():
     return _PPMLink()
 
 
+# ------------------------------------------------------------------------------------------------ fused PSA attention
+class _PSAAttend(torch.autograd.Function):
+    """psa_mask -> softmax over the source positions -> aggregation bmm -> 1/normalization_factor (model/psanet.py:81-91)
+    as one kernel each way; nothing [HW x HW] is written to HBM (the backward recomputes the probabilities from the
+    logits and the saved per-target (max, 1/sum))."""
+
+    @staticmethod
+    def forward(ctx, attn, feat, psa_type, mask_h, mask_w, scale):
+        out, stats = ops.psa_attend(attn, feat, psa_type, mask_h, mask_w, scale)
+        ctx.save_for_backward(attn, feat, out, stats)
+        ctx.cfg = (psa_type, mask_h, mask_w, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        attn, feat, out, stats = ctx.saved_tensors
+        psa_type, mask_h, mask_w, scale = ctx.cfg
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        dattn = dfeat = None
+        if ctx.needs_input_grad[1]:
+            dfeat, _ = ops.psa_attend(attn, dout, psa_type, mask_h, mask_w, scale, stats=stats, mode=1)
+        if ctx.needs_input_grad[0]:
+            dattn = ops.psa_attend_bwd_attn(attn, stats, feat, out, dout, psa_type, mask_h, mask_w, scale)
+        return dattn, dfeat, None, None, None, None
+
+
+def psa_attend(attn, feat, psa_type, mask_h, mask_w, scale):
+    """attn fp32 NHWC [N,h,w,mask_h*mask_w], feat NHWC activation [N,h,w,512] -> aggregated features [N,h,w,512]."""
+    return _PSAAttend.apply(attn.contiguous(), feat, psa_type, mask_h, mask_w, scale)
+
+
+def psa_attend_supported(feat, mask_h, mask_w):
+    return feat.shape[-1] == 512 and feat.shape[-2] <= 128 and mask_h % 2 == 1 and mask_w % 2 == 1
+
+
+# ------------------------------------------------------------------------------------------------ bilinear resize
+class _ResizeBilinear(torch.autograd.Function):
+    """F.interpolate(mode='bilinear', align_corners=True) on an NHWC activation (model/psanet.py:61,97), deterministic
+    gather backward."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        ctx.in_size = tuple(x.shape[-3:-1])
+        return ops.resize_bilinear(x, size)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.resize_bilinear_bwd(dy if dy.is_contiguous() else dy.contiguous(), ctx.in_size), None
+
+
+def resize_bilinear(x, size):
+    return _ResizeBilinear.apply(x, tuple(size))
+
+
 # ------------------------------------------------------------------------------------------------ misc NHWC ops
 def to_nhwc_bf16(x_nchw):
     """fp32 NCHW module input -> NHWC activation (channels padded to a multiple of 8 with zeros) in the storage form of

@@ -91,8 +91,18 @@ def _sync_bn_ready(model):
 def _capture(model, impl, st, x, y):
     global _capturing
     from . import _lib
-    params = [p for p in model.parameters() if p.requires_grad]
-    st.params = params
+    # Parameter proxies: the backward graph is captured with torch.autograd.grad w.r.t. FRESH leaves that alias the
+    # parameters' storage. The real parameters' AccumulateGrad nodes may be kept alive from earlier eager iterations (by a
+    # loss tensor, or by DistributedDataParallel, which stashes them at construction) and are bound to the stream they
+    # were created on; letting the capture deliver gradients to them would make that (legacy) stream depend on the
+    # capturing stream, which CUDA forbids (cudaErrorStreamCaptureImplicit).
+    slots, seen = [], set()
+    for mod in model.modules():
+        for name, prm in mod._parameters.items():
+            if prm is not None and prm.requires_grad and id(prm) not in seen:
+                seen.add(id(prm))
+                slots.append((mod, name, prm))
+    st.params = [prm for _, _, prm in slots]
     st.x, st.y = torch.empty_like(x), torch.empty_like(y)
     st.x.copy_(x)
     st.y.copy_(y)
@@ -101,21 +111,31 @@ def _capture(model, impl, st, x, y):
     st.fwd, st.bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
     l0 = _lib.launch_count()
     _capturing = True
+    proxies = []
     try:
+        for mod, name, prm in slots:
+            q = prm.detach().requires_grad_(True)      # same storage, new leaf
+            mod._parameters[name] = q
+            proxies.append(q)
         with torch.cuda.graph(st.fwd, pool=st.pool, capture_error_mode="thread_local"):
             with torch.enable_grad():
                 st.pred, st.main, st.aux = impl(st.x, st.y)
         st.g_main, st.g_aux = torch.ones_like(st.main), torch.ones_like(st.aux)
         with torch.cuda.graph(st.bwd, pool=st.pool, capture_error_mode="thread_local"):
-            st.grads = torch.autograd.grad((st.main, st.aux), params, (st.g_main, st.g_aux), allow_unused=True)
+            st.grads = torch.autograd.grad((st.main, st.aux), proxies, (st.g_main, st.g_aux), allow_unused=True)
     finally:
         _capturing = False
+        for mod, name, prm in slots:
+            mod._parameters[name] = prm
     st.launches = _lib.launch_count() - l0          # native kernels per replayed step (forward + backward graphs)
-    # drop the autograd graph built during capture (its AccumulateGrad nodes are bound to the capture stream and would
-    # be kept alive by the loss tensors); the static outputs live on in the graphs' private memory pool
+    # drop the autograd graph built during capture; the static outputs live on in the graphs' private memory pool
     st.pred, st.main, st.aux = st.pred.detach(), st.main.detach(), st.aux.detach()
+    del proxies
     # the graphs reference the persistent weight slabs: keep their owner alive as long as the graphs
     st.keep = model.__dict__.get("_sb_pack_plan")
+    # per-conv pack caches were keyed on the proxies' version counters during capture: forget them
+    for mod in model.modules():
+        mod.__dict__.pop("_sb_pack_patches", None)
     torch.cuda.synchronize()
 
 
@@ -144,6 +164,8 @@ def train_step(model, impl, x, y):
             _capture(model, impl, st, x, y)
         except Exception as e:      # noqa: BLE001 - stay on the eager path (same kernels), say so once
             st.failed, st.fwd = True, None
+            if os.environ.get("SEMSEG_B200_GRAPH_DEBUG"):
+                raise
             warnings.warn("semseg_b200: CUDA-graph capture of the training step failed (%s: %s); continuing eagerly" %
                           (type(e).__name__, str(e).splitlines()[0][:200] if str(e) else ""))
             torch.cuda.synchronize()

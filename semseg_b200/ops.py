@@ -111,6 +111,40 @@ def psamask_bwd(grad_out, psa_type, mask_h, mask_w):
     return din
 
 
+# ------------------------------------------------------------------------------------------------ fused PSA attention
+def psa_attend(attn, feat, psa_type, mask_h, mask_w, scale, stats=None, mode=0):
+    """mode 0: (out, stats) = fused mask-gather -> softmax -> aggregation (model/psanet.py:81-91) of the fp32 NHWC logits
+    `attn` [N,h,w,>=mask_h*mask_w] and the NHWC activation `feat` [N,h,w,512]; mode 1: the feature gradient (pass dout as
+    `feat` and the forward's `stats`)."""
+    _require_cuda(attn, feat)
+    lib = _lib.load()
+    assert attn.dtype == torch.float32 and attn.dim() == 4 and attn.is_contiguous()
+    n, h, w, c, fp = _nhwc_meta(feat)
+    assert tuple(attn.shape[:3]) == (n, h, w) and attn.shape[3] >= mask_h * mask_w
+    out = empty_act((n, h, w, c), is_split(feat), feat.device)
+    if stats is None:
+        assert mode == 0
+        stats = torch.empty((n, h * w, 2), dtype=torch.float32, device=feat.device)
+    _lib.check(lib.semseg_psa_attend(mode, psa_type, _ptr(attn), attn.shape[3], _ptr(feat), _lo(feat), fp, _ptr(stats),
+                                     _ptr(out), _lo(out), c, n, h, w, mask_h, mask_w, c, float(scale), _stream()),
+               "semseg_psa_attend")
+    return out, stats
+
+
+def psa_attend_bwd_attn(attn, stats, feat, out, dout, psa_type, mask_h, mask_w, scale):
+    """Gradient of psa_attend w.r.t. the attention logits (same shape as attn, zero outside the mask windows)."""
+    lib = _lib.load()
+    n, h, w, c, fp = _nhwc_meta(feat)
+    op, dp = _nhwc_meta(out)[4], _nhwc_meta(dout)[4]
+    _same_form(feat, out, dout)
+    dattn = torch.empty_like(attn)
+    _lib.check(lib.semseg_psa_attend_bwd_attn(psa_type, _ptr(attn), attn.shape[3], _ptr(stats), _ptr(feat), _lo(feat), fp,
+                                              _ptr(out), _lo(out), op, _ptr(dout), _lo(dout), dp, _ptr(dattn), n, h, w,
+                                              mask_h, mask_w, c, float(scale), _stream()),
+               "semseg_psa_attend_bwd_attn")
+    return dattn
+
+
 # ------------------------------------------------------------------------------------------------ weights
 class PackedWeight:
     """bf16 operand slabs of one conv weight: wf [taps][Cout][Cin_p] (fprop), wd [taps][Cin][Cout_p] (dgrad); with
@@ -674,6 +708,30 @@ def ppm_upsample_bwd(dout, c_off, bins, cr):
     _lib.check(lib.semseg_ppm_upsample_bwd(_ptr(dout), _lo(dout), p, c_off, parr, larr, barr, nb, n, h, w, cr,
                                            _stream()), "semseg_ppm_upsample_bwd")
     return dfeats
+
+
+# ------------------------------------------------------------------------------------------------ bilinear resize
+def resize_bilinear(x, size):
+    """NHWC activation [N,Hi,Wi,C] -> [N,Ho,Wo,C], bilinear with align_corners=True."""
+    _require_cuda(x)
+    lib = _lib.load()
+    n, hi, wi, c, p = _nhwc_meta(x)
+    ho, wo = int(size[0]), int(size[1])
+    y = empty_act((n, ho, wo, c), is_split(x), x.device)
+    _lib.check(lib.semseg_resize_bilinear_fwd(_ptr(x), _lo(x), p, n, hi, wi, c, ho, wo, _ptr(y), _lo(y), c, _stream()),
+               "semseg_resize_bilinear_fwd")
+    return y
+
+
+def resize_bilinear_bwd(dy, in_size):
+    """Adjoint of resize_bilinear: dy [N,Ho,Wo,C] -> dx [N,Hi,Wi,C]."""
+    lib = _lib.load()
+    n, ho, wo, c, p = _nhwc_meta(dy)
+    hi, wi = int(in_size[0]), int(in_size[1])
+    dx = empty_act((n, hi, wi, c), is_split(dy), dy.device)
+    _lib.check(lib.semseg_resize_bilinear_bwd(_ptr(dy), _lo(dy), p, n, hi, wi, c, ho, wo, _ptr(dx), _lo(dx), c, _stream()),
+               "semseg_resize_bilinear_bwd")
+    return dx
 
 
 # ------------------------------------------------------------------------------------------------ max pool

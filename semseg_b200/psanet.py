@@ -5,6 +5,8 @@ The point-wise spatial attention block keeps the reference's arithmetic order: r
 bilinear shrink -> attention (1x1+BN+ReLU, 1x1) -> psa_mask collect/distribute -> softmax over the
 H*W source positions -> aggregation bmm -> proj -> bilinear upsample -> concat.
 """
+import os
+
 import torch
 from torch import nn
 import torch.nn.functional as F
@@ -19,13 +21,8 @@ from .pspnet import head_forward_nhwc, upsample_logits
 
 
 def _interp_nhwc(x, size):
-    """bilinear (align_corners=True) resize of an NHWC activation (model/psanet.py:61,97): fp32 arithmetic for split
-    activations, bf16 for plain ones."""
-    if ops.is_split(x):
-        y = F.interpolate(SF.act_to_f32(x).permute(0, 3, 1, 2), size=size, mode='bilinear', align_corners=True)
-        return SF.f32_to_act(y.permute(0, 2, 3, 1).contiguous(), True)
-    y = F.interpolate(x.permute(0, 3, 1, 2), size=size, mode='bilinear', align_corners=True)
-    return y.permute(0, 2, 3, 1).contiguous()
+    """bilinear (align_corners=True) resize of an NHWC activation (model/psanet.py:61,97) on the native kernel."""
+    return SF.resize_bilinear(x, size)
 
 
 class PSA(nn.Module):
@@ -85,6 +82,11 @@ class PSA(nn.Module):
         t, t_agg = SF.fork(t, 2)                              # t feeds the attention convs and the aggregation
         a = SF.conv_bn_act(t, attention[0], attention[1], relu=True)
         y = SF.conv_bias_f32(a, attention[3])                 # fp32 NHWC [n,h,w,mask_h*mask_w]
+        if (self.psa_softmax and not self.compact and SF.psa_attend_supported(t_agg, self.mask_h, self.mask_w)
+                and os.environ.get("SEMSEG_B200_PSA_FUSED", "1") != "0"):
+            # one kernel: mask gather -> softmax over the h*w source positions -> aggregation -> 1/normalization_factor
+            # (model/psanet.py:81-91); the [n, hw, hw] attention map is never written to HBM
+            return SF.psa_attend(y, t_agg, mask_type, self.mask_h, self.mask_w, 1.0 / self.normalization_factor), (h, w)
         y = y.permute(0, 3, 1, 2).contiguous()                # NCHW fp32, the layout psa_mask is defined on
         if self.compact:
             if mask_type == 1:

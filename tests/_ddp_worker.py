@@ -9,8 +9,9 @@ by rank 0 in one process over the CONCATENATED batch — not against this reposi
       vs the oracle's per-shard cross-entropy (SURVEY.md §8 e: each rank's CE is a mean over its own valid pixels),
       running statistics, and DDP-averaged head gradients vs d/dθ of mean_r(loss_r).
 
-Tolerances depend on the operand mode (argv[1]): bf16x3 -> 1e-4 forward / 1e-3 gradients; bf16 -> the single-pass bf16
-floors used by tests/test_parity_gpu.py. Prints one line per check and exits non-zero on any failure.
+Tolerances depend on the operand mode (argv[1]): bf16x3 -> 1e-4 forward, 1e-5 running statistics, gradients to the ReLU
+mask-flip floor (1e-2 against the plain oracle; the mask-matched 1e-3 check lives in tests/test_parity_x3_gpu.py);
+bf16 -> the single-pass bf16 floors used by tests/test_parity_gpu.py. Prints one line per check and exits non-zero on any failure.
 """
 import copy
 import os
@@ -48,7 +49,9 @@ def block_checks(rank, world, dev, mode):
     from semseg_b200.pspnet import PPM
     from oracle.torch_oracle import Oracle
     x3 = mode == "bf16x3"
-    tol_y, tol_g, tol_run = (1e-4, 1e-3, 1e-5) if x3 else (8e-3, 0.15, 2e-4)
+    # gradients against the PLAIN fp32 oracle: the ReLU mask-flip floor sqrt(0.8 * forward error) applies
+    # (tests/test_parity_x3_gpu.py::test_bottleneck_block_x3_vs_oracle), ~3e-3 at a forward error of 1e-5
+    tol_y, tol_g, tol_run = (1e-4, 1e-2, 1e-5) if x3 else (8e-3, 0.15, 2e-4)
     ok, per = True, 2
     torch.manual_seed(1)
     ds = nn.Sequential(nn.Conv2d(256, 512, 1, bias=False), nn.BatchNorm2d(512))

@@ -79,3 +79,44 @@ def test_peer_exchange_slot_sequence_and_nccl_override(monkeypatch):
     monkeypatch.setenv("SEMSEG_B200_SYNCBN", "nccl")
     assert p2p.get_exchange(object()) is None
     assert p2p.exchange_kind() == "none"        # no process group initialised in this process
+
+
+def _log_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from semseg_b200.train_utils import reduce_step_logging
+    try:
+        k = 7
+        g = torch.Generator().manual_seed(rank)
+        ml, al = torch.rand((), generator=g) + 1, torch.rand((), generator=g) + 1
+        loss = ml + 0.4 * al
+        n = 3 + rank
+        inter, union, tgt = (torch.randint(0, 50, (k,), generator=g).float() for _ in range(3))
+        # the reference's seven all-reduces (tool/train.py:280-288)
+        r_ml, r_al, r_loss = ml * n, al * n, loss * n
+        cnt = torch.tensor([n], dtype=torch.long)
+        ri, ru, rt = inter.clone(), union.clone(), tgt.clone()
+        for t in (r_ml, r_al, r_loss, cnt, ri, ru, rt):
+            dist.all_reduce(t)
+        m = reduce_step_logging(ml, al, loss, n, inter, union, tgt)
+        ok = (torch.allclose(m.main_loss, r_ml / cnt.item(), rtol=1e-6) and torch.allclose(m.aux_loss, r_al / cnt.item(), rtol=1e-6)
+              and torch.allclose(m.loss, r_loss / cnt.item(), rtol=1e-6) and int(m.n) == cnt.item()
+              and torch.equal(m.intersection, ri) and torch.equal(m.union, ru) and torch.equal(m.target, rt))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_step_logging_single_allreduce_matches_the_references_seven_world2():
+    """one packed all-reduce == the reference's seven (tool/train.py:278-289), world size 2 on gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_log_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p_ in procs:
+        p_.join(60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -633,3 +633,63 @@ def test_intersection_and_union_kernel_exact():
         assert np.array_equal(o.cpu().numpy().reshape(-1), masked)          # the reference masks `output` in place
     with pytest.raises(Exception):
         intersectionAndUnionGPU(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 3)
+
+
+# ------------------------------------------------------------------------------------------------ fused PSA attention
+@pytest.mark.parametrize("geom", [(2, 30, 30, 59, 59), (1, 9, 12, 9, 7), (2, 13, 13, 25, 25), (1, 5, 40, 9, 79)])
+@pytest.mark.parametrize("psa_type", [0, 1])
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3"])
+def test_psa_attend_fused_vs_mask_softmax_bmm(geom, psa_type, mode):
+    """the fused gather -> softmax -> aggregation kernels (forward, feature gradient, attention-logit
+    gradient) against the reference composition psa_mask -> softmax(dim=1) -> bmm (model/psanet.py:81-91) in fp32 torch,
+    including masks smaller than the full 2H-1 x 2W-1 window (out-of-window logits are zeros that still enter the softmax)."""
+    from semseg_b200 import functional as SF, ops
+    from lib.psa.functional import psa_mask
+    n, h, w, mh, mw = geom
+    c, scale = 512, 1.0 / 3.0
+    split = mode == "bf16x3"
+    g = torch.Generator(device="cuda").manual_seed(h * 100 + w + psa_type)
+    attn = (torch.randn((n, h, w, mh * mw), device="cuda", generator=g) * 2).requires_grad_(True)
+    f32 = torch.relu(torch.randn((n, h, w, c), device="cuda", generator=g))
+    feat = (ops.f32_to_act(f32, True) if split else f32.to(torch.bfloat16)).requires_grad_(True)
+    go32 = torch.randn((n, h, w, c), device="cuda", generator=g)
+    go = ops.f32_to_act(go32, True) if split else go32.to(torch.bfloat16)
+    out = SF.psa_attend(attn, feat, psa_type, mh, mw, scale)
+    out.backward(go)
+    # reference composition on the same (rounded) values
+    ar = attn.detach().clone().requires_grad_(True)
+    fr = ops.act_to_f32(feat.detach()).requires_grad_(True)
+    y = psa_mask(ar.permute(0, 3, 1, 2).contiguous(), psa_type, mh, mw)            # [n, hw, h, w], zero outside the window
+    y = torch.softmax(y, dim=1)
+    ref = torch.bmm(fr.view(n, h * w, c).transpose(1, 2), y.view(n, h * w, h * w)) * scale     # [n, c, hw]
+    ref = ref.transpose(1, 2).reshape(n, h, w, c)
+    ref.backward(ops.act_to_f32(go))
+    tol_f, tol_g = (3e-5, 1e-4) if split else (4e-3, 1e-2)
+    assert util.rel_l2(ops.act_to_f32(out), ref) < tol_f
+    assert util.rel_l2(ops.act_to_f32(feat.grad), fr.grad) < tol_g
+    assert util.rel_l2(attn.grad, ar.grad) < tol_g
+    # entries of the logits that no (target, source) pair reads get exactly zero gradient
+    assert bool(((ar.grad == 0) <= (attn.grad == 0)).all())
+
+
+@pytest.mark.parametrize("geom", [(2, 59, 59, 30, 30), (2, 30, 30, 59, 59), (1, 7, 11, 20, 5), (1, 1, 1, 6, 6), (2, 9, 9, 9, 9)])
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3"])
+def test_resize_bilinear_vs_torch(geom, mode):
+    """NHWC bilinear resize (align_corners=True; model/psanet.py:61,97) and its gather adjoint vs F.interpolate in fp32."""
+    from semseg_b200 import functional as SF, ops
+    n, hi, wi, ho, wo = geom
+    c = 64
+    split = mode == "bf16x3"
+    g = torch.Generator(device="cuda").manual_seed(hi * 10 + wo)
+    x32 = torch.randn((n, hi, wi, c), device="cuda", generator=g)
+    x = (ops.f32_to_act(x32, True) if split else x32.to(torch.bfloat16)).requires_grad_(True)
+    go32 = torch.randn((n, ho, wo, c), device="cuda", generator=g)
+    go = ops.f32_to_act(go32, True) if split else go32.to(torch.bfloat16)
+    y = SF.resize_bilinear(x, (ho, wo))
+    y.backward(go)
+    xr = ops.act_to_f32(x.detach()).permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.interpolate(xr, size=(ho, wo), mode="bilinear", align_corners=True)
+    yr.backward(ops.act_to_f32(go).permute(0, 3, 1, 2))
+    tol = 2e-5 if split else 4e-3
+    assert util.rel_l2(ops.act_to_f32(y), yr.permute(0, 2, 3, 1)) < tol
+    assert util.rel_l2(ops.act_to_f32(x.grad), xr.grad.permute(0, 2, 3, 1)) < tol

@@ -44,7 +44,7 @@ def main():
         loss.backward()
         opt.step()
 
-    for _ in range(3):
+    for _ in range(8):          # eager warm-up + (unless SEMSEG_B200_GRAPH=0) capture of the step graphs
         step()
     torch.cuda.synchronize()
     if args.ncu:
