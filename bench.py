@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stock-gpu", action="store_true")
     ap.add_argument("--no-parity-mode", action="store_true")
+    ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
+                    help="torch.optim.SGD (the reference's, tool/train.py:140) or semseg_b200.optim.FusedSGD (one launch)")
     return ap.parse_args()
 
 
@@ -110,12 +112,15 @@ def synth_batch(n, size, classes, seed):
     return x, y
 
 
-def build_optimizer(model, arch):
+def build_optimizer(model, arch, kind="torch"):
     """The reference's 8 SGD parameter groups (tool/train.py:125-140)."""
     import torch
     ori = [model.layer0, model.layer1, model.layer2, model.layer3, model.layer4]
     new = [model.ppm if arch == "psp" else model.psa, model.cls, model.aux]
     groups = [dict(params=m.parameters(), lr=0.01) for m in ori] + [dict(params=m.parameters(), lr=0.1) for m in new]
+    if kind == "fused":
+        from semseg_b200.optim import FusedSGD
+        return FusedSGD(groups, lr=0.01, momentum=0.9, weight_decay=1e-4)
     return torch.optim.SGD(groups, lr=0.01, momentum=0.9, weight_decay=1e-4)
 
 
@@ -260,7 +265,7 @@ def run_b200_arm(args):
         mk = 2 * ((args.size - 1) // 16 + 1) - 1
         model = PSANet(layers=args.layers, classes=args.classes, zoom_factor=8, mask_h=mk, mask_w=mk,
                        pretrained=False)
-    opt = build_optimizer(model, args.arch)
+    opt = build_optimizer(model, args.arch, args.optimizer)
     if world > 1:
         model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
         model = nn.parallel.DistributedDataParallel(model.cuda(), device_ids=[local_rank])
@@ -400,7 +405,9 @@ def run_b200_arm(args):
         "config": {"workload": workload_name(args),
                    "global_batch": args.batch * world, "parallelism": "dp%d" % world,
                    "l2": "inputs larger than L2: each step streams > 10 GB of activations through the 126 MB L2",
-                   "optimizer": "SGD momentum 0.9 wd 1e-4, 8 param groups", "sync_bn": world > 1,
+                   "optimizer": "%s, momentum 0.9 wd 1e-4, 8 param groups" % (
+                       "torch.optim.SGD" if args.optimizer == "torch" else "semseg_b200.optim.FusedSGD (one launch)"),
+                   "sync_bn": world > 1,
                    "execution": ("forward and backward replayed as two CUDA graphs (%d kernels per step) behind one "
                                  "autograd node" % graphed) if graphed else "eager launches",
                    "syncbn_exchange": __import__("semseg_b200.p2p", fromlist=["x"]).exchange_kind()},

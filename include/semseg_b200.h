@@ -362,6 +362,34 @@ int semseg_upsample_ce_bwd(const float* logits, int pitch, int N, int h, int w, 
 int semseg_iou_hist(void* pred_i64, const void* target_i64, long long n, int K, long long ignore_index, int write_back,
                     int* counts, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * torch.optim.SGD (momentum, dampening, weight decay, nesterov; tool/train.py:140,274-276) over every parameter tensor in
+ * one launch. items_dev: device array sorted by chunk0 (an item's chunks are consecutive blocks of
+ * semseg_sgd_chunk_elems() elements); grad_ptrs_dev: device array of n_items gradient pointers (0 = no gradient this
+ * step: the parameter is skipped); hyper: per-group hyper-parameters, passed by value. `first` != 0 initialises the
+ * momentum buffer with the (decayed) gradient, as torch does on a parameter's first step.
+ */
+#define SEMSEG_SGD_MAX_GROUPS 16
+typedef struct semseg_sgd_item {
+  float* w;
+  float* buf;
+  long long n;
+  int group;
+  int chunk0;
+  int first;
+  int reserved;
+} semseg_sgd_item;
+typedef struct semseg_sgd_hyper {
+  float lr[SEMSEG_SGD_MAX_GROUPS];
+  float momentum[SEMSEG_SGD_MAX_GROUPS];
+  float weight_decay[SEMSEG_SGD_MAX_GROUPS];
+  float dampening[SEMSEG_SGD_MAX_GROUPS];
+  int nesterov;
+} semseg_sgd_hyper;
+int semseg_sgd_chunk_elems(void);
+int semseg_sgd_multi(const semseg_sgd_item* items_dev, const void* grad_ptrs_dev, int n_items, int n_chunks,
+                     const semseg_sgd_hyper* hyper, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,18 @@ class PackItem(ctypes.Structure):
     ]
 
 
+class SgdItem(ctypes.Structure):
+    """struct semseg_sgd_item (include/semseg_b200.h)."""
+    _fields_ = [("w", c_vp), ("buf", c_vp), ("n", c_ll), ("group", c_i32), ("chunk0", c_i32), ("first", c_i32),
+                ("reserved", c_i32)]
+
+
+class SgdHyper(ctypes.Structure):
+    """struct semseg_sgd_hyper (include/semseg_b200.h)."""
+    _fields_ = [("lr", c_f * 16), ("momentum", c_f * 16), ("weight_decay", c_f * 16), ("dampening", c_f * 16),
+                ("nesterov", c_i32)]
+
+
 class ConvDesc(ctypes.Structure):
     """struct semseg_conv_desc (include/semseg_b200.h)."""
     _fields_ = [
@@ -95,6 +107,8 @@ SIGNATURES = {
     "semseg_wgrad_reduce": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "semseg_pack_weights": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp]),
     "semseg_pack_weights_multi": (c_int, [c_vp, c_int, c_int, c_int, c_vp]),
+    "semseg_sgd_chunk_elems": (c_int, []),
+    "semseg_sgd_multi": (c_int, [c_vp, c_vp, c_int, c_int, ctypes.POINTER(SgdHyper), c_vp]),
     "semseg_iou_hist": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_int, ctypes.c_longlong, c_int, c_vp, c_vp]),
     "semseg_im2col3x3s2": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "semseg_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

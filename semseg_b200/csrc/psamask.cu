@@ -18,12 +18,13 @@ namespace sb {
 // TYPE 0 = collect, 1 = distribute. grid = N*H*H blocks (n, h, i).
 template <int TYPE>
 __global__ void __launch_bounds__(128) psamask_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                          int N, int H, int W, int mH, int mW) {
+                                                          int N, int H, int W, int mH, int mW, int h_fastest) {
   extern __shared__ float S[];
   const int hh = (mH - 1) / 2, hw = (mW - 1) / 2;
   const int P = TYPE == 0 ? ((W | 1) + 1) : (W | 1);
-  const int i = blockIdx.x % H;
-  const int h = (blockIdx.x / H) % H;
+  // block order: with h fastest, concurrently running blocks write the 30 adjacent rows of the same output planes
+  const int i = h_fastest ? (blockIdx.x / H) % H : blockIdx.x % H;
+  const int h = h_fastest ? blockIdx.x % H : (blockIdx.x / H) % H;
   const int n = blockIdx.x / (H * H);
   const int a = i - h + hh;
   const bool a_ok = a >= 0 && a < mH;
@@ -58,12 +59,12 @@ __global__ void __launch_bounds__(128) psamask_fwd_kernel(const float* __restric
 // grid = N*H*mH blocks (n, h, a): writes the whole din slab [mW][W] (zeros where nothing maps).
 template <int TYPE>
 __global__ void __launch_bounds__(128) psamask_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din,
-                                                          int N, int H, int W, int mH, int mW) {
+                                                          int N, int H, int W, int mH, int mW, int h_fastest) {
   extern __shared__ float S[];
   const int hh = (mH - 1) / 2, hw = (mW - 1) / 2;
   const int P = (W | 1) + 1;
-  const int a = blockIdx.x % mH;
-  const int h = (blockIdx.x / mH) % H;
+  const int a = h_fastest ? (blockIdx.x / H) % mH : blockIdx.x % mH;
+  const int h = h_fastest ? blockIdx.x % H : (blockIdx.x / mH) % H;
   const int n = blockIdx.x / (mH * H);
   const int i = a + h - hh;
   const bool i_ok = i >= 0 && i < H;
@@ -86,6 +87,11 @@ __global__ void __launch_bounds__(128) psamask_bwd_kernel(const float* __restric
     if (i_ok && j >= 0 && j < W) v = TYPE == 0 ? S[j * P + w] : S[w * P + j];
     dst[static_cast<size_t>(b) * HW + w] = v;
   }
+}
+
+static int psa_h_fastest() {
+  const char* e = getenv("SEMSEG_B200_PSA_ORDER");     // re-read every call: the bench A/Bs the two orders in one run
+  return (e && e[0] == '0') ? 0 : 1;
 }
 
 static int check_psa(int psa_type, const void* a, const void* b, int N, int H, int W, int mH, int mW) {
@@ -111,11 +117,11 @@ extern "C" int semseg_psamask_fwd(int psa_type, const float* in, float* out, int
   if (psa_type == 0) {
     if (smem > 48 * 1024)
       SB_CUDA(cudaFuncSetAttribute(psamask_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    psamask_fwd_kernel<0><<<grid, 128, smem, stream>>>(in, out, N, H, W, mH, mW);
+    psamask_fwd_kernel<0><<<grid, 128, smem, stream>>>(in, out, N, H, W, mH, mW, psa_h_fastest());
   } else {
     if (smem > 48 * 1024)
       SB_CUDA(cudaFuncSetAttribute(psamask_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    psamask_fwd_kernel<1><<<grid, 128, smem, stream>>>(in, out, N, H, W, mH, mW);
+    psamask_fwd_kernel<1><<<grid, 128, smem, stream>>>(in, out, N, H, W, mH, mW, psa_h_fastest());
   }
   SB_LAUNCHED();
   return SEMSEG_OK;
@@ -134,11 +140,11 @@ extern "C" int semseg_psamask_bwd(int psa_type, const float* dout, float* din, i
   if (psa_type == 0) {
     if (smem > 48 * 1024)
       SB_CUDA(cudaFuncSetAttribute(psamask_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    psamask_bwd_kernel<0><<<grid, 128, smem, stream>>>(dout, din, N, H, W, mH, mW);
+    psamask_bwd_kernel<0><<<grid, 128, smem, stream>>>(dout, din, N, H, W, mH, mW, psa_h_fastest());
   } else {
     if (smem > 48 * 1024)
       SB_CUDA(cudaFuncSetAttribute(psamask_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    psamask_bwd_kernel<1><<<grid, 128, smem, stream>>>(dout, din, N, H, W, mH, mW);
+    psamask_bwd_kernel<1><<<grid, 128, smem, stream>>>(dout, din, N, H, W, mH, mW, psa_h_fastest());
   }
   SB_LAUNCHED();
   return SEMSEG_OK;

@@ -29,6 +29,7 @@ from . import precision
 
 WARMUP_CALLS = 3          # eager calls with an unchanged key before capturing
 _capturing = False
+_boundary = None          # activation noted by the model during capture: where the backward is cut in two
 
 
 def enabled():
@@ -41,12 +42,39 @@ def capturing():
     return _capturing
 
 
+def note_boundary(t):
+    """Called by the model's forward while a step is being captured: `t` (the activation entering the dilated stages)
+    cuts the backward pass into two graphs — everything after it (heads, layer4, layer3: 97 % of the parameters) and
+    everything before it (stem, layer1, layer2). The first graph's parameter gradients are handed to autograd (and to
+    DDP's bucket hooks: their all-reduce starts) while the second graph still computes, which restores the
+    communication / computation overlap a single backward graph would lose."""
+    global _boundary
+    if _capturing and t.requires_grad:
+        _boundary = t
+    return t
+
+
 class _Step:
-    __slots__ = ("key", "calls", "failed", "fwd", "bwd", "x", "y", "pred", "main", "aux", "g_main", "g_aux", "grads",
-                 "params", "pool", "keep", "launches")
+    __slots__ = ("key", "calls", "failed", "fwd", "bwd", "bwd2", "x", "y", "pred", "main", "aux", "g_main", "g_aux",
+                 "grads", "grads2", "t_mid", "d_mid", "n_tail", "params", "pool", "keep", "launches")
 
     def __init__(self, key):
         self.key, self.calls, self.failed, self.fwd = key, 0, False, None
+
+
+def _set_grad_outputs(st, g_main, g_aux):
+    if g_main is None:
+        st.g_main.zero_()
+    else:
+        st.g_main.copy_(g_main)
+    if g_aux is None:
+        st.g_aux.zero_()
+    else:
+        st.g_aux.copy_(g_aux)
+
+
+def _detached(gs):
+    return tuple(g.detach() if g is not None else None for g in gs)
 
 
 class _Replay(torch.autograd.Function):
@@ -66,16 +94,49 @@ class _Replay(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _g_pred, g_main, g_aux):
         st = ctx.st
-        if g_main is None:
-            st.g_main.zero_()
-        else:
-            st.g_main.copy_(g_main)
-        if g_aux is None:
-            st.g_aux.zero_()
-        else:
-            st.g_aux.copy_(g_aux)
+        _set_grad_outputs(st, g_main, g_aux)
         st.bwd.replay()
-        return (None, None, None) + tuple(g.detach() if g is not None else None for g in st.grads)
+        return (None, None, None) + _detached(st.grads)
+
+
+class _ReplayHead(torch.autograd.Function):
+    """Two-segment form, first node: replays the whole forward graph, returns the boundary activation; its backward
+    replays the SECOND backward graph (stem, layer1, layer2) from the boundary gradient the tail node left in place."""
+
+    @staticmethod
+    def forward(ctx, st, x, y, *params_head):
+        st.x.copy_(x, non_blocking=True)
+        st.y.copy_(y, non_blocking=True)
+        st.fwd.replay()
+        ctx.st = st
+        return st.t_mid.detach()
+
+    @staticmethod
+    def backward(ctx, d_mid):
+        st = ctx.st
+        if d_mid.data_ptr() != st.d_mid.data_ptr():
+            st.d_mid.copy_(d_mid)
+        st.bwd2.replay()
+        return (None, None, None) + _detached(st.grads2)
+
+
+class _ReplayTail(torch.autograd.Function):
+    """Two-segment form, second node: hands out the static outputs; its backward replays the FIRST backward graph
+    (heads, layer4, layer3) and returns the boundary gradient plus those parameters' gradients."""
+
+    @staticmethod
+    def forward(ctx, st, t_mid, *params_tail):
+        ctx.st = st
+        pred, main, aux = st.pred.detach(), st.main.detach(), st.aux.detach()
+        ctx.mark_non_differentiable(pred)
+        return pred, main, aux
+
+    @staticmethod
+    def backward(ctx, _g_pred, g_main, g_aux):
+        st = ctx.st
+        _set_grad_outputs(st, g_main, g_aux)
+        st.bwd.replay()
+        return (None, st.d_mid) + _detached(st.grads)
 
 
 def _sync_bn_ready(model):
@@ -108,9 +169,10 @@ def _capture(model, impl, st, x, y):
     st.y.copy_(y)
     torch.cuda.synchronize()
     st.pool = torch.cuda.graph_pool_handle()
-    st.fwd, st.bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    st.fwd, st.bwd, st.bwd2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), None
     l0 = _lib.launch_count()
-    _capturing = True
+    global _boundary
+    _capturing, _boundary = True, None
     proxies = []
     try:
         for mod, name, prm in slots:
@@ -121,10 +183,31 @@ def _capture(model, impl, st, x, y):
             with torch.enable_grad():
                 st.pred, st.main, st.aux = impl(st.x, st.y)
         st.g_main, st.g_aux = torch.ones_like(st.main), torch.ones_like(st.aux)
-        with torch.cuda.graph(st.bwd, pool=st.pool, capture_error_mode="thread_local"):
-            st.grads = torch.autograd.grad((st.main, st.aux), proxies, (st.g_main, st.g_aux), allow_unused=True)
+        t_mid = _boundary
+        head_ids = set()
+        if t_mid is not None and os.environ.get("SEMSEG_B200_GRAPH_SEGMENTS", "2") != "1":
+            for name in getattr(model, "_sb_head_modules", ()):
+                head_ids.update(id(q) for q in getattr(model, name).parameters())
+        if head_ids:
+            # parameters reordered: head (before the boundary) first, tail after
+            order = [k for k, q in enumerate(proxies) if id(q) in head_ids] + \
+                    [k for k, q in enumerate(proxies) if id(q) not in head_ids]
+            n_head = len(head_ids)
+            st.params = [st.params[k] for k in order]
+            prox_head = [proxies[k] for k in order[:n_head]]
+            prox_tail = [proxies[k] for k in order[n_head:]]
+            with torch.cuda.graph(st.bwd, pool=st.pool, capture_error_mode="thread_local"):
+                gs = torch.autograd.grad((st.main, st.aux), [t_mid] + prox_tail, (st.g_main, st.g_aux), allow_unused=True)
+            st.d_mid, st.grads = gs[0], gs[1:]
+            st.bwd2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st.bwd2, pool=st.pool, capture_error_mode="thread_local"):
+                st.grads2 = torch.autograd.grad((t_mid,), prox_head, (st.d_mid,), allow_unused=True)
+            st.t_mid, st.n_tail = t_mid.detach(), len(prox_tail)
+        else:
+            with torch.cuda.graph(st.bwd, pool=st.pool, capture_error_mode="thread_local"):
+                st.grads = torch.autograd.grad((st.main, st.aux), proxies, (st.g_main, st.g_aux), allow_unused=True)
     finally:
-        _capturing = False
+        _capturing, _boundary = False, None
         for mod, name, prm in slots:
             mod._parameters[name] = prm
     st.launches = _lib.launch_count() - l0          # native kernels per replayed step (forward + backward graphs)
@@ -170,6 +253,10 @@ def train_step(model, impl, x, y):
                           (type(e).__name__, str(e).splitlines()[0][:200] if str(e) else ""))
             torch.cuda.synchronize()
             return None
+    if st.bwd2 is not None:
+        n_head = len(st.params) - st.n_tail
+        t_mid = _ReplayHead.apply(st, x, y, *st.params[:n_head])
+        return _ReplayTail.apply(st, t_mid, *st.params[n_head:])
     return _Replay.apply(st, x, y, *st.params)
 
 

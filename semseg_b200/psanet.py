@@ -175,6 +175,8 @@ class PSANet(nn.Module):
                 nn.Conv2d(256, classes, kernel_size=1)
             )
 
+    _sb_head_modules = ("layer0", "layer1", "layer2")     # modules whose parameters lie before graphs.note_boundary
+
     def forward(self, x, y=None):
         x_size = x.size()
         assert (x_size[2] - 1) % 8 == 0 and (x_size[3] - 1) % 8 == 0
@@ -197,7 +199,7 @@ class PSANet(nn.Module):
         t = SF.to_nhwc_bf16(x)
         t = self.layer0.forward_nhwc(t)
         t = self.layer1.forward_nhwc(t)
-        t = self.layer2.forward_nhwc(t)
+        t = graphs.note_boundary(self.layer2.forward_nhwc(t))     # where a captured backward is cut in two
         t_tmp = self.layer3.forward_nhwc(t)
         t_aux = None
         if self.training:       # layer3's output feeds layer4 and the aux head: explicit fan-out (native gradient add)

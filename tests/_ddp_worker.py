@@ -51,7 +51,7 @@ def block_checks(rank, world, dev, mode):
     x3 = mode == "bf16x3"
     # gradients against the PLAIN fp32 oracle: the ReLU mask-flip floor sqrt(0.8 * forward error) applies
     # (tests/test_parity_x3_gpu.py::test_bottleneck_block_x3_vs_oracle), ~3e-3 at a forward error of 1e-5
-    tol_y, tol_g, tol_run = (1e-4, 1e-2, 1e-5) if x3 else (8e-3, 0.15, 2e-4)
+    tol_y, tol_g, tol_run = (1e-4, 1e-2, 1e-5) if x3 else (8e-3, 0.15, 1e-2)
     ok, per = True, 2
     torch.manual_seed(1)
     ds = nn.Sequential(nn.Conv2d(256, 512, 1, bias=False), nn.BatchNorm2d(512))
@@ -157,7 +157,7 @@ def network_check(rank, world, local, dev, mode):
         dsd = ddp.module.state_dict()
         worst = max((rel(dsd[k], sd[k]), k) for k in sd if "running" in k)
         print("worst running-stat rel err vs oracle %.3e (%s)" % worst)
-        ok &= worst[0] < (1e-3 if x3 else 3e-2)
+        ok &= worst[0] < (1e-3 if x3 else 1e-1)
         # the classifier layers sit downstream of everything: their DDP-averaged gradients vs the oracle
         dp = dict(ddp.module.named_parameters())
         for k in ("cls.4.weight", "cls.4.bias", "aux.4.weight", "aux.4.bias"):

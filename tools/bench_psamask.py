@@ -60,8 +60,13 @@ def main():
         for t, name in ((0, "collect"), (1, "distribute")):
             fwd_bytes = 2 * 4 * n * (h * w) ** 2
             bwd_bytes = 4 * n * (h * w) ** 2 + 4 * n * mh * mw * h * w
+            os.environ["SEMSEG_B200_PSA_ORDER"] = "0"           # A/B of the block order (i fastest vs h fastest)
+            alt_f = timeit(lambda: ops.psamask_fwd(x, t, mh, mw), flush)
+            alt_b = timeit(lambda: ops.psamask_bwd(g, t, mh, mw), flush)
+            os.environ["SEMSEG_B200_PSA_ORDER"] = "1"
             ours_f = timeit(lambda: ops.psamask_fwd(x, t, mh, mw), flush)
             ours_b = timeit(lambda: ops.psamask_bwd(g, t, mh, mw), flush)
+            print("   block order i-fastest: fwd %.4f bwd %.4f ms | h-fastest (default): fwd %.4f bwd %.4f ms" % (alt_f, alt_b, ours_f, ours_b))
             row = {"n": n, "type": name, "ours_fwd_ms": ours_f, "ours_bwd_ms": ours_b,
                    "ours_fwd_gbs": fwd_bytes / ours_f / 1e6, "ours_bwd_gbs": bwd_bytes / ours_b / 1e6}
             if stock is not None:

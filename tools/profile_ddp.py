@@ -35,7 +35,7 @@ def main():
         loss.backward()
         opt.step()
 
-    for _ in range(4):
+    for _ in range(9):          # eager warm-up + capture of the step graphs (unless SEMSEG_B200_GRAPH=0)
         step()
     torch.cuda.synchronize()
     dist.barrier()
