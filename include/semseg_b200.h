@@ -240,7 +240,8 @@ int semseg_bn_finalize_partials(const float* stats_partial, int rows, int C, con
                                 void* stream);
 /* SyncBatchNorm exchange over NVLink peer memory instead of NCCL (one kernel per exchange). peer_bufs[world] /
  * peer_flags[world] are device pointers into every rank's symmetric (peer-mapped) allocation: a float buffer of
- * n_slots*slot_floats and a zero-initialised uint32 flag array [n_slots][world]; `counter` is a zeroed local uint32;
+ * n_slots*world*slot_floats (every rank PUSHES its block into sub-block `rank` of the slot in every peer's buffer and
+ * merges from its own memory) and a zero-initialised uint32 flag array [n_slots][world]; `counter` is a zeroed local uint32;
  * `slot` must be unique per exchange within a step and the sequence number strictly increasing per step (same on every
  * rank): it is `seq`, or — when seq_ptr is non-NULL — the uint32 read from that device address when the kernel runs (a
  * device-resident step counter, so that a captured CUDA graph with baked-in slots can be replayed).

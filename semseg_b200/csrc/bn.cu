@@ -799,19 +799,24 @@ __global__ void __launch_bounds__(1024) bn_finalize_p2p_kernel(const float* __re
   __shared__ Moments sm[32][CH + 1];
   const Moments own_m = block_conv_moments<CH>(part, T, C, blockIdx.x * CH, sm);
   const int c_own = blockIdx.x * CH + (threadIdx.x >> 5);
-  const size_t off = static_cast<size_t>(pa.slot) * pa.slot_floats;
+  // PUSH exchange: every rank stores its (mean, M2, n) block straight into sub-block `rank` of the slot in EVERY peer's
+  // buffer (posted NVLink stores, no round trip); after the flags arrive each rank merges from its own local memory.
+  const size_t slot0 = static_cast<size_t>(pa.slot) * pa.world * pa.slot_floats;
   if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < CH && c_own < C) {
-    float* own = pa.buf[pa.rank] + off;
-    own[c_own] = own_m.mean;
-    own[C + c_own] = own_m.m2;
-    own[2 * C + c_own] = own_m.n;
+    const size_t off = slot0 + static_cast<size_t>(pa.rank) * pa.slot_floats;
+    for (int p = 0; p < pa.world; ++p) {
+      float* dst = pa.buf[p] + off;
+      dst[c_own] = own_m.mean;
+      dst[C + c_own] = own_m.m2;
+      dst[2 * C + c_own] = own_m.n;
+    }
   }
   if (!peer_publish_and_wait(pa)) return;
-  // last block of this rank: every rank's (mean, M2, n) block is published -> merge in rank order and finalise all channels
+  // last block of this rank: every rank's block has landed in local memory -> merge in rank order, finalise all channels
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     Moments r = {0.f, 0.f, 0.f};
     for (int p = 0; p < pa.world; ++p) {
-      const float* b = pa.buf[p] + off;
+      const float* b = pa.buf[pa.rank] + slot0 + static_cast<size_t>(p) * pa.slot_floats;
       Moments m;
       m.mean = ld_relaxed_sys(b + c);
       m.m2 = ld_relaxed_sys(b + C + c);
@@ -859,17 +864,19 @@ __global__ void __launch_bounds__(1024) bn_bwd_reduce_final_p2p_kernel(const flo
   }
   sm[tl][cl] = acc;
   __syncthreads();
-  const size_t off = static_cast<size_t>(pa.slot) * pa.slot_floats;
+  const size_t slot0 = static_cast<size_t>(pa.slot) * pa.world * pa.slot_floats;
   if (tl == 0 && idx < 2 * C) {
     float r = 0.f;
     for (int i = 0; i < 32; ++i) r += sm[i][cl];
     sums_local[idx] = r;
-    pa.buf[pa.rank][off + idx] = r;
+    const size_t off = slot0 + static_cast<size_t>(pa.rank) * pa.slot_floats + idx;
+    for (int p = 0; p < pa.world; ++p) pa.buf[p][off] = r;      // push to every peer (and to myself)
   }
   if (!peer_publish_and_wait(pa)) return;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {   // last block: all ranks published -> totals for every channel
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {   // last block: all ranks' blocks are local -> totals, rank order
     float r = 0.f;
-    for (int p = 0; p < pa.world; ++p) r += ld_relaxed_sys(pa.buf[p] + off + i);
+    for (int p = 0; p < pa.world; ++p)
+      r += ld_relaxed_sys(pa.buf[pa.rank] + slot0 + static_cast<size_t>(p) * pa.slot_floats + i);
     sums_total[i] = r;
   }
 }

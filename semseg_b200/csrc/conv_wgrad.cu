@@ -428,13 +428,24 @@ static void wgrad_geometry(const semseg_wgrad_desc* d, WgradKParams* kp) {
   const int units = kp->unit_taps * kp->co_tiles * kp->ci_tiles;
   int splits = d->n_splits;
   if (splits <= 0) {
-    // aim for >= 2 waves of work units over the SMs, but keep >= 16 K-blocks per unit
-    const int target = 2 * num_sms() / (kp->pair ? 2 : 1);
-    splits = cdiv(target, units);
+    // Split-K factor: the work units (units x splits) run on `slots` CTAs (clusters in pair mode) in whole rounds, so
+    // the last round should be (nearly) full — 9 taps x 17 splits = 153 units on 74 clusters is 3 rounds at 69 %, x 16 is
+    // 2 rounds at 97 % — while every unit keeps enough K blocks to amortise its pipeline fill / TMEM drain (~8 blocks).
+    const int slots = num_sms() / (kp->pair ? 2 : 1);
     const int max_by_k = kp->num_boxes / 16 > 0 ? kp->num_boxes / 16 : 1;
-    if (splits > max_by_k) splits = max_by_k;
-    if (splits > 64) splits = 64;
-    if (splits < 1) splits = 1;
+    const int max_s = max_by_k < 64 ? max_by_k : 64;
+    double best = -1.0;
+    splits = 1;
+    for (int sp = 1; sp <= max_s; ++sp) {
+      const double waves = static_cast<double>(units) * sp / slots;
+      const double rounds = ceil(waves);
+      const double kb = static_cast<double>(kp->num_boxes) / sp;
+      const double score = (waves / rounds) * (kb / (kb + 8.0)) * (waves >= 1.0 ? 1.0 : waves);
+      if (score > best + 1e-9) {
+        best = score;
+        splits = sp;
+      }
+    }
     if (d->x_lo != nullptr) {
       // bf16x3: bound one accumulation chain to 21 pixel boxes (21 x 4 MMA steps x 3 segments = 252 steps): the tensor
       // core's fp32 accumulation truncates (~2^-24 per step towards zero, tools/probe_accum.py); the fixed-order fp32

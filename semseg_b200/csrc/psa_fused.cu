@@ -39,7 +39,8 @@ constexpr int kPfStageBytes = kPfABytes + kPfBBytes;
 constexpr int kPfStages = 2;
 constexpr int kPfWorkers = 256;                   // warps 2..9
 constexpr int kPfThreads = 64 + kPfWorkers;
-constexpr int kPfSmem = kPfStages * kPfStageBytes + 4096 + 1024;
+constexpr int kPfMisc = 256 + 2 * kPfRows * 4 + 2 * 8 * kPfRows * 4;   // barriers, row stats, per-warp partial stats
+constexpr int kPfSmem = kPfStages * kPfStageBytes + kPfMisc + 1024;
 
 struct PsaFusedParams {
   const float* A;       // [N][Q][a_pitch]
@@ -99,6 +100,12 @@ psa_attend_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  // rows of the 128-row A tile that do not exist in this CTA's tile stay zero for the whole kernel
+  for (int s = 0; s < kPfStages; ++s) {
+    uint4* a4 = reinterpret_cast<uint4*>(smem + s * kPfStageBytes);
+    for (int i = threadIdx.x; i < kPfABytes / 16; i += kPfThreads) a4[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -177,19 +184,38 @@ psa_attend_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
           }
         }
       } else {
-        // distribute: row = target, one entry of every source vector; consecutive rows read consecutive addresses
-        // -> one thread per row, online softmax over the sources
-        if (wt < kPfRows) {
-          const int r = wt;
+        // distribute: row = target, one entry of every source vector; consecutive rows read consecutive addresses ->
+        // lanes along rows, the sources split over the 8 worker warps (online softmax), partials merged through smem
+        float* pm = reinterpret_cast<float*>(misc + 256 + 2 * kPfRows * 4);   // [8][128] partial max
+        float* ps = pm + 8 * kPfRows;                                           // [8][128] partial sum
+        const int q_per = (Q + 7) / 8, q0 = ww * q_per, q1 = min(Q, q0 + q_per);
+        for (int r = lane; r < kPfRows; r += 32) {
           float m = -INFINITY, sum = 0.f;
           if (r < live_rows) {
             const int ri = row_i0 + r / p.W, rj = r % p.W;
-            for (int q = 0; q < Q; ++q) {
+            for (int q = q0; q < q1; ++q) {
               const float l = pf_logit(An, p.a_pitch, q, q / p.W, q % p.W, ri, rj, hh, hw, p.mH, p.mW);
               const float mn = fmaxf(m, l);
               sum = sum * __expf(m - mn) + __expf(l - mn);
               m = mn;
             }
+          }
+          pm[ww * kPfRows + r] = m;
+          ps[ww * kPfRows + r] = sum;
+        }
+        named_bar_sync(1, kPfWorkers);
+        if (wt < kPfRows) {
+          const int r = wt;
+          float m = -INFINITY, sum = 0.f;
+          if (r < live_rows) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m = fmaxf(m, pm[k * kPfRows + r]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float mk = pm[k * kPfRows + r];
+              if (mk > -INFINITY) sum += ps[k * kPfRows + r] * __expf(mk - m);
+            }
+            const int ri = row_i0 + r / p.W, rj = r % p.W;
             stats_n[ri * p.W + rj] = make_float2(m, 1.f / sum);
           }
           s_m[r] = m;
@@ -207,54 +233,43 @@ psa_attend_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       uint8_t* a_st = smem + s * kPfStageBytes;
       const bool want_lo = seg == 1;
       if (kRowOwner) {
-        // the row pixel owns the attention vector -> addresses are contiguous along k: warp per row, lanes along k
+        // the row pixel owns the attention vector -> addresses are contiguous along k: one warp per (row, 32-column
+        // half), lanes along k; the live (row, half) items are dealt round-robin to the 8 worker warps
         // [forward collect, dfeat distribute]
-        for (int r = ww; r < kPfRows; r += kPfWorkers / 32) {
-          const bool r_ok = r < live_rows;
+        for (int item = ww; item < 2 * live_rows; item += kPfWorkers / 32) {
+          const int r = item >> 1, half = item & 1;
           const int ri = row_i0 + r / p.W, rj = r % p.W, rpos = ri * p.W + rj;
-          float rm = 0.f, rinv = 0.f;
-          if (kStatsRow) {
-            rm = s_m[r];
-            rinv = s_inv[r];
-          }
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int kl = half * 32 + lane, q = kb * kPfK + kl;
-            float pv = 0.f;
-            if (r_ok && q < Q) {
-              const int qi = q / p.W, qj = q - qi * p.W;
-              const float l = pf_logit(An, p.a_pitch, rpos, ri, rj, qi, qj, hh, hw, p.mH, p.mW);
-              if (kStatsRow) {
-                pv = __expf(l - rm) * rinv;
-              } else {
-                const float2 st = stats_n[q];
-                pv = __expf(l - st.x) * st.y;
-              }
+          const int kl = half * 32 + lane, q = kb * kPfK + kl;
+          float pv = 0.f;
+          if (q < Q) {
+            const int qi = q / p.W, qj = q - qi * p.W;
+            const float l = pf_logit(An, p.a_pitch, rpos, ri, rj, qi, qj, hh, hw, p.mH, p.mW);
+            if (kStatsRow) {
+              pv = __expf(l - s_m[r]) * s_inv[r];
+            } else {
+              const float2 st = stats_n[q];
+              pv = __expf(l - st.x) * st.y;
             }
-            __nv_bfloat16 hi = __float2bfloat16_rn(pv);
-            if (want_lo) hi = __float2bfloat16_rn(pv - __bfloat162float(hi));
-            *reinterpret_cast<__nv_bfloat16*>(a_st + r * 128 + (((kl >> 3) ^ (r & 7)) << 4) + (kl & 7) * 2) = hi;
           }
+          __nv_bfloat16 hi = __float2bfloat16_rn(pv);
+          if (want_lo) hi = __float2bfloat16_rn(pv - __bfloat162float(hi));
+          *reinterpret_cast<__nv_bfloat16*>(a_st + r * 128 + (((kl >> 3) ^ (r & 7)) << 4) + (kl & 7) * 2) = hi;
         }
       } else {
-        // the k pixel owns the vector -> addresses are contiguous along the row index: lanes along rows, every thread owns
-        // one row and half of the k columns  [forward distribute, dfeat collect]
-        const int r = wt & (kPfRows - 1), khalf = wt >> 7;   // 256 workers = 128 rows x 2 column halves
-        const bool r_ok = r < live_rows;
-        const int ri = row_i0 + r / p.W, rj = r % p.W;
-        float rm = 0.f, rinv = 0.f;
-        if (kStatsRow) {
-          rm = s_m[r];
-          rinv = s_inv[r];
-        }
-        for (int kk = 0; kk < 32; ++kk) {
-          const int kl = khalf * 32 + kk, q = kb * kPfK + kl;
+        // the k pixel owns the vector -> addresses are contiguous along the row index: lanes along rows; the
+        // (32-row group, k column) items are dealt round-robin to the 8 worker warps  [forward distribute, dfeat collect]
+        const int row_groups = (live_rows + 31) >> 5;
+        for (int item = ww; item < row_groups * kPfK; item += kPfWorkers / 32) {
+          const int rg = item % row_groups, kl = item / row_groups;
+          const int r = rg * 32 + lane, q = kb * kPfK + kl;
+          if (r >= live_rows) continue;
           float pv = 0.f;
-          if (r_ok && q < Q) {
+          if (q < Q) {
+            const int ri = row_i0 + r / p.W, rj = r % p.W;
             const int qi = q / p.W, qj = q - qi * p.W;
             const float l = pf_logit(An, p.a_pitch, q, qi, qj, ri, rj, hh, hw, p.mH, p.mW);
             if (kStatsRow) {
-              pv = __expf(l - rm) * rinv;
+              pv = __expf(l - s_m[r]) * s_inv[r];
             } else {
               const float2 st = stats_n[q];
               pv = __expf(l - st.x) * st.y;
@@ -341,7 +356,14 @@ extern "C" int semseg_psa_attend(int mode, int psa_type, const float* attn, int 
   p.A = attn; p.stats = reinterpret_cast<float2*>(stats);
   p.out = static_cast<__nv_bfloat16*>(out); p.out_lo = static_cast<__nv_bfloat16*>(out_lo); p.out_pitch = out_pitch;
   p.N = N; p.H = H; p.W = W; p.mH = mH; p.mW = mW; p.a_pitch = a_pitch;
+  // grid rows per CTA: at most 128 / W, fewer when that leaves SMs idle (the tensor-core work is negligible, the
+  // per-row gather / exp work of the workers is what takes the time)
   p.rows_per_tile = kPfRows / W;
+  {
+    const int want = (N * H) / num_sms();
+    const int rpt = want < 1 ? 1 : want;
+    if (rpt < p.rows_per_tile) p.rows_per_tile = rpt;
+  }
   p.tiles_per_img = cdiv(H, p.rows_per_tile);
   p.nseg = feat_lo ? 3 : 1;
   p.scale = scale;
@@ -419,7 +441,9 @@ psa_attn_grad_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_cons
   const int live_rows = min(p.rows_per_tile, p.H - row_i0) * p.W;
   const int hh = (p.mH - 1) / 2, hw = (p.mW - 1) / 2;
   const int k_blocks = p.C / 64;
-  const int n_blocks = (Q + kPgBlockN - 1) / kPgBlockN;
+  // one 256-source block per CTA (blockIdx.y): the per-element epilogue (recompute P, scatter) dominates, so the source
+  // blocks of a target tile run on different SMs
+  const int nb_first = blockIdx.y, nb_last = blockIdx.y + 1;
   const int per_nb = k_blocks * p.nseg;
 
   if (warp == 0 && lane == 0) {
@@ -444,7 +468,7 @@ psa_attn_grad_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_cons
   if (warp == 0) {
     if (elect_one()) {
       int it = 0;
-      for (int nb = 0; nb < n_blocks; ++nb) {
+      for (int nb = nb_first; nb < nb_last; ++nb) {
         for (int kk = 0; kk < per_nb; ++kk, ++it) {
           const int s = it % kPgStages;
           const uint32_t par = (it / kPgStages) & 1;
@@ -471,9 +495,9 @@ psa_attn_grad_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_cons
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, kPgBlockN, 0, 0);   // both operands K-major
       int it = 0;
-      for (int nb = 0; nb < n_blocks; ++nb) {
-        const int as = nb & 1;
-        mbar_wait(&tmem_empty[as], ((nb >> 1) & 1) ^ 1);
+      for (int nb = nb_first; nb < nb_last; ++nb) {
+        const int as = (nb - nb_first) & 1;
+        mbar_wait(&tmem_empty[as], (((nb - nb_first) >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kPgBlockN);
         for (int kk = 0; kk < per_nb; ++kk, ++it) {
@@ -522,9 +546,9 @@ psa_attn_grad_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_cons
       rm = st.x;
       rinv = st.y;
     }
-    for (int nb = 0; nb < n_blocks; ++nb) {
-      const int as = nb & 1;
-      mbar_wait(&tmem_full[as], (nb >> 1) & 1);
+    for (int nb = nb_first; nb < nb_last; ++nb) {
+      const int as = (nb - nb_first) & 1;
+      mbar_wait(&tmem_full[as], ((nb - nb_first) >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
@@ -573,7 +597,8 @@ static int launch_attn_grad(const CUtensorMap& a, const CUtensorMap& al, const C
     SB_CUDA(cudaFuncSetAttribute(psa_attn_grad_kernel<kCollect>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPgSmem));
     if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
   }
-  psa_attn_grad_kernel<kCollect><<<grid, kPgThreads, kPgSmem, stream>>>(a, al, b, bl, p);
+  const dim3 g(grid, cdiv(p.H * p.W, kPgBlockN));
+  psa_attn_grad_kernel<kCollect><<<g, kPgThreads, kPgSmem, stream>>>(a, al, b, bl, p);
   SB_LAUNCHED();
   return SEMSEG_OK;
 }
@@ -603,6 +628,11 @@ extern "C" int semseg_psa_attend_bwd_attn(int psa_type, const float* attn, int a
   p.dout_pitch = dout_pitch; p.out_pitch = out_pitch;
   p.N = N; p.H = H; p.W = W; p.mH = mH; p.mW = mW; p.a_pitch = a_pitch; p.C = C;
   p.rows_per_tile = 128 / W;
+  {
+    const int want = (N * H * cdiv(H * W, kPgBlockN)) / num_sms();     // keep every SM busy (rows <-> epilogue threads)
+    const int rpt = want < 1 ? 1 : want;
+    if (rpt < p.rows_per_tile) p.rows_per_tile = rpt;
+  }
   p.tiles_per_img = cdiv(H, p.rows_per_tile);
   p.nseg = split ? 3 : 1;
   p.scale = scale;

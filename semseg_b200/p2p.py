@@ -1,8 +1,8 @@
 """SyncBatchNorm statistics exchange over NVLink peer memory (torch symmetric memory).
 
 One process per GPU; every rank allocates the same symmetric buffer, `rendezvous` maps all peers' buffers into this
-process, and the exchange kernels (csrc/bn.cu: bn_finalize_p2p, bn_bwd_reduce_p2p) publish / flag / read directly over
-NVLink — one kernel per BatchNorm exchange instead of merge-kernel + NCCL collective + finalise-kernel.
+process, and the exchange kernels (csrc/bn.cu: bn_finalize_p2p, bn_bwd_reduce_p2p) push their block into every peer's
+buffer, raise a flag there and merge from local memory once the peers' flags have arrived — all over NVLink — one kernel per BatchNorm exchange instead of merge-kernel + NCCL collective + finalise-kernel.
 If symmetric memory cannot be set up (no P2P access, single process, SEMSEG_B200_SYNCBN=nccl) the callers use the
 NCCL path (torch.distributed all_gather / all_reduce); both paths compute the same statistics.
 """
@@ -12,8 +12,8 @@ import os
 import torch
 import torch.distributed as dist
 
-N_SLOTS = 512
-SLOT_FLOATS = 3 * 4096          # (mean, M2, n) for up to 4096 channels
+N_SLOTS = 256                   # exchanges per epoch (PSPNet101: 224 per step); more simply open a new epoch
+SLOT_FLOATS = 3 * 4096          # one rank's block: (mean, M2, n) for up to 4096 channels; a slot holds `world` of them
 
 _exchanges = {}
 
@@ -27,7 +27,7 @@ class PeerExchange:
             raise RuntimeError("peer exchange supports up to 8 ranks (one NVSwitch domain)")
         dev = torch.device("cuda", torch.cuda.current_device())
         flag_words = N_SLOTS * self.world
-        self.buf = symm_mem.empty(flag_words + N_SLOTS * SLOT_FLOATS, dtype=torch.float32, device=dev)
+        self.buf = symm_mem.empty(flag_words + N_SLOTS * self.world * SLOT_FLOATS, dtype=torch.float32, device=dev)
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, pg)
         ptrs = [int(p) for p in self.handle.buffer_ptrs]

@@ -55,7 +55,7 @@ def test_graphed_steps_bit_identical_to_eager(arch, monkeypatch):
         assert torch.equal(eager(batches[0][0]), graphed(batches[0][0]))
     # another input shape: eager warm-up again, then a second captured step; training continues to work
     graphed.train()
-    other = [util.synth(2, 73, 73, 21, seed=9, device="cuda")]
+    other = [util.synth(2, 81, 81, 21, seed=9, device="cuda")]     # 81 -> 11x11 maps (PSA's 2x shrink needs an odd size)
     l2 = _steps(graphed, other, graphs.WARMUP_CALLS + 2)
     assert all(torch.isfinite(torch.tensor(v)).all() for v in l2)
     assert len([s for s in graphed.__dict__["_sb_graph_steps"].values() if s.fwd is not None]) == 2
