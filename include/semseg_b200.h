@@ -229,7 +229,8 @@ int semseg_bn_stats(const void* x, int M, int C, int pitch, float* workspace, lo
 /* Scratch floats the two-stage reductions (bn_stats, bn_bwd_reduce) need for an [M][C] tensor. */
 long long semseg_bn_workspace_floats(int M, int C);
 /* Merge R rank-stat blocks [R][3][C] (R = 1 without SyncBN) and finalise:
- *   mean_invstd [2][C]; scale_shift [2][C] with scale = gamma*invstd, shift = beta - mean*scale;
+ *   mean_invstd [3][C] = (mean, 1/sqrt(var+eps), total samples per channel over all ranks — every finalize entry point
+ *   writes the three rows); scale_shift [2][C] with scale = gamma*invstd, shift = beta - mean*scale;
  *   running_mean/var updated in place (momentum, unbiased var) when non-NULL. */
 int semseg_bn_finalize(const float* rank_stats, int R, int C, const float* gamma, const float* beta, float eps,
                        float momentum, float* running_mean, float* running_var, float* mean_invstd,
@@ -239,9 +240,10 @@ int semseg_bn_finalize_partials(const float* stats_partial, int rows, int C, con
                                 float* running_mean, float* running_var, float* mean_invstd, float* scale_shift,
                                 void* stream);
 /* SyncBatchNorm exchange over NVLink peer memory instead of NCCL (one kernel per exchange). peer_bufs[world] /
- * peer_flags[world] are device pointers into every rank's symmetric (peer-mapped) allocation: a float buffer of
- * n_slots*world*slot_floats (every rank PUSHES its block into sub-block `rank` of the slot in every peer's buffer and
- * merges from its own memory) and a zero-initialised uint32 flag array [n_slots][world]; `counter` is a zeroed local uint32;
+ * peer_flags[world] are device pointers into every rank's symmetric (peer-mapped) allocation: a zero-initialised buffer
+ * of n_slots*world*slot_floats 8-byte words (every value travels as one {fp32, sequence number} word that the sender
+ * stores into sub-block `rank` of the slot in every peer's buffer; the receiver polls its own memory: flag-in-data, no
+ * fences) and a uint32 flag array [n_slots][world] (unused by this protocol, kept for ABI stability); `counter` is a zeroed local uint32;
  * `slot` must be unique per exchange within a step and the sequence number strictly increasing per step (same on every
  * rank): it is `seq`, or — when seq_ptr is non-NULL — the uint32 read from that device address when the kernel runs (a
  * device-resident step counter, so that a captured CUDA graph with baked-in slots can be replayed).
@@ -274,7 +276,8 @@ int semseg_bn_bwd_reduce(const void* dy, const void* dy_lo, int dy_pitch, const 
                          long long workspace_floats, float* sums, void* stream);
 /* Backward apply: dx = gamma*invstd*(dz - sum_dz/count - xhat*sum_dzxhat/count);
  *   dres (optional) = dz; dgamma = sum_dzxhat, dbeta = sum_dz written to dgamma_dbeta [2][C].
- *   count = total number of samples per channel across all ranks. */
+ *   count = total number of samples per channel across all ranks; count <= 0 takes it from mean_invstd row 2 (what
+ *   the forward exchange measured: correct also when the ranks hold different numbers of pixels, as torch SyncBN). */
 int semseg_bn_bwd_apply(const void* dy, const void* dy_lo, int dy_pitch, const void* y, const void* y_lo, int y_pitch,
                         const void* x, const void* x_lo, int x_pitch, const float* mean_invstd, const float* gamma,
                         const float* scale_shift, const float* sums, float count, int M, int C, int relu, void* dx,

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float*
     const float invstd = rsqrtf(var + eps);
     mean_invstd[c] = r.mean;
     mean_invstd[C + c] = invstd;
+    mean_invstd[2 * C + c] = r.n;     // samples per channel over all ranks (the backward's 1/count)
     const float sc = (gamma ? gamma[c] : 1.f) * invstd;
     scale_shift[c] = sc;
     scale_shift[C + c] = (beta ? beta[c] : 0.f) - r.mean * sc;
@@ -259,6 +260,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ rs, int R, int C, c
   const float invstd = rsqrtf(var + eps);
   mean_invstd[c] = acc.mean;
   mean_invstd[C + c] = invstd;
+  mean_invstd[2 * C + c] = acc.n;
   const float g = gamma ? gamma[c] : 1.f;
   const float bt = beta ? beta[c] : 0.f;
   const float sc = g * invstd;
@@ -515,8 +517,9 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
     const float mean = mean_invstd[c], invstd = mean_invstd[C + c];
     const float g = gamma ? gamma[c] : 1.f;
     ka[q] = g * invstd;
-    kx[q] = -ka[q] * invstd * sums[C + c] * inv_count;
-    kb[q] = -ka[q] * sums[c] * inv_count - kx[q] * mean;
+    const float ic = inv_count > 0.f ? inv_count : 1.f / mean_invstd[2 * C + c];   // count <= 0: the exchanged total
+    kx[q] = -ka[q] * invstd * sums[C + c] * ic;
+    kb[q] = -ka[q] * sums[c] * ic - kx[q] * mean;
   }
   auto finish = [&](float (&d)[8], const float (&xv)[8], const float (&yv)[8], long long pp) {
     if (mask_from_y) {
@@ -725,9 +728,9 @@ __global__ void act_to_f32_kernel(const __nv_bfloat16* __restrict__ in, const __
 // flags and then reads their blocks directly over NVLink. One kernel per exchange, no NCCL call, no stream hop;
 // the cross-rank merge is done in rank order on every rank, so all ranks compute bit-identical statistics.
 struct PeerArgs {
-  float* buf[8];        // peer-mapped data buffers (buf[rank] is local)
-  unsigned* flags[8];   // peer-mapped flag arrays [slots][world]
-  unsigned* counter;    // local block-arrival counter (self-resetting)
+  float* buf[8];        // peer-mapped data buffers (buf[rank] is local): 8-byte {value, seq} words, [slot][src rank][slot_floats]
+  unsigned* flags[8];   // (unused by the LL protocol; kept in the ABI)
+  unsigned* counter;    // (unused by the LL protocol)
   int world, rank, slot, slot_floats;
   unsigned seq;         // sequence number of this exchange: the value of *seq_ptr when seq_ptr is given, else `seq`
   const unsigned* seq_ptr;  // device-resident step counter (lets a captured CUDA graph be replayed: the slot is baked
@@ -749,48 +752,33 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
   return v;
 }
 
-// Spin limit of the cross-rank wait in clock64 ticks (~2 GHz): default 10 minutes, like a collective library's watchdog
-// (a debugger, a host stall or a straggler on one rank must not kill the other ranks' CUDA contexts after seconds);
-// SEMSEG_B200_P2P_TIMEOUT_S overrides it. Set by the host wrappers through PeerArgs::timeout_ticks.
-//
-// Exchange protocol (called by every thread of every block after the block's own data has been stored to buf[rank]):
-// every block counts itself in; ONLY THE LAST block of this rank's grid goes on — it raises this rank's flag in every
-// peer's flag array, waits for the peers' flags and returns true; all other blocks return false and exit. So exactly one
-// block per rank ever spins: no co-residency requirement between the blocks of the grid, and nothing that an NCCL kernel
-// sharing the SMs could dead-lock with. The caller's last block then does the cross-rank merge for ALL
-// channels (a few thousand values, over NVLink).
-__device__ __forceinline__ bool peer_publish_and_wait(const PeerArgs& pa) {
-  __shared__ int s_last;
-  const unsigned seq = pa.seq_ptr ? *pa.seq_ptr : pa.seq;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();                       // my block's stores to buf[rank] are visible system-wide ...
-    const unsigned prev = atomicAdd(pa.counter, 1u);
-    s_last = (prev == gridDim.x - 1) ? 1 : 0;     // ... before the last arriver publishes the flag
-  }
-  __syncthreads();
-  if (!s_last) return false;
-  if (threadIdx.x == 0) {
-    *pa.counter = 0u;
-    __threadfence_system();
-    for (int p = 0; p < pa.world; ++p) st_release_sys(pa.flags[p] + pa.slot * pa.world + pa.rank, seq);
-  }
-  if (threadIdx.x < pa.world) {
-    const unsigned* f = pa.flags[pa.rank] + pa.slot * pa.world + threadIdx.x;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(f) != seq) {
-      if (clock64() - t0 > pa.timeout_ticks) {  // a peer that never arrives must not hang the GPU forever
-        printf("semseg_b200: SyncBN peer exchange timed out (rank %d waiting for rank %d, slot %d, seq %u)\n", pa.rank,
-               static_cast<int>(threadIdx.x), pa.slot, seq);
-        __trap();
-      }
+// Exchange protocol ("LL", flag-in-data): a value travels as ONE 8-byte word {fp32 bits, sequence number}. The sender
+// stores the word straight into sub-block `rank` of the slot in EVERY peer's buffer (posted NVLink stores); the receiver
+// polls the word in its OWN memory until the sequence number matches. 8-byte stores are single transactions, so there is
+// no separate flag, no system-scope fence, no cross-block counter: every thread that finishes a channel exchanges that
+// channel on its own, the latency is one NVLink store, and a block only ever waits for data that peers push without
+// needing any of this GPU's SMs (no co-residency requirement, nothing an NCCL kernel sharing the SMs can dead-lock with).
+// A peer that never arrives trips the watchdog (default 10 minutes, SEMSEG_B200_P2P_TIMEOUT_S) instead of hanging the GPU.
+__device__ __forceinline__ void st_ll(unsigned long long* p, float v, unsigned seq) {
+  const unsigned long long w = (static_cast<unsigned long long>(seq) << 32) | __float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ float ld_ll(const unsigned long long* p, unsigned seq, const PeerArgs& pa, int peer) {
+  unsigned long long w;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    if (static_cast<unsigned>(w >> 32) == seq) break;
+    if (clock64() - t0 > pa.timeout_ticks) {
+      printf("semseg_b200: SyncBN peer exchange timed out (rank %d waiting for rank %d, slot %d, seq %u)\n", pa.rank, peer,
+             pa.slot, seq);
+      __trap();
     }
   }
-  __syncthreads();
-  return true;
+  return __uint_as_float(static_cast<unsigned>(w & 0xffffffffu));
 }
 
-// Forward: merge this rank's conv partials, exchange (mean, M2, n), merge over ranks, finalise.
+// Forward: merge this rank's conv partials, exchange (mean, M2, n), merge over ranks in rank order, finalise.
 template <int CH>
 __global__ void __launch_bounds__(1024) bn_finalize_p2p_kernel(const float* __restrict__ part, int T, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, float momentum,
@@ -798,43 +786,41 @@ __global__ void __launch_bounds__(1024) bn_finalize_p2p_kernel(const float* __re
                                        float* __restrict__ mean_invstd, float* __restrict__ scale_shift, PeerArgs pa) {
   __shared__ Moments sm[32][CH + 1];
   const Moments own_m = block_conv_moments<CH>(part, T, C, blockIdx.x * CH, sm);
-  const int c_own = blockIdx.x * CH + (threadIdx.x >> 5);
-  // PUSH exchange: every rank stores its (mean, M2, n) block straight into sub-block `rank` of the slot in EVERY peer's
-  // buffer (posted NVLink stores, no round trip); after the flags arrive each rank merges from its own local memory.
+  const int c = blockIdx.x * CH + (threadIdx.x >> 5);
+  if (!((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < CH && c < C)) return;   // this thread finishes channel c
+  const unsigned seq = pa.seq_ptr ? *pa.seq_ptr : pa.seq;
   const size_t slot0 = static_cast<size_t>(pa.slot) * pa.world * pa.slot_floats;
-  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < CH && c_own < C) {
+  {
     const size_t off = slot0 + static_cast<size_t>(pa.rank) * pa.slot_floats;
     for (int p = 0; p < pa.world; ++p) {
-      float* dst = pa.buf[p] + off;
-      dst[c_own] = own_m.mean;
-      dst[C + c_own] = own_m.m2;
-      dst[2 * C + c_own] = own_m.n;
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(pa.buf[p]) + off;
+      st_ll(dst + c, own_m.mean, seq);
+      st_ll(dst + C + c, own_m.m2, seq);
+      st_ll(dst + 2 * C + c, own_m.n, seq);
     }
   }
-  if (!peer_publish_and_wait(pa)) return;
-  // last block of this rank: every rank's block has landed in local memory -> merge in rank order, finalise all channels
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    Moments r = {0.f, 0.f, 0.f};
-    for (int p = 0; p < pa.world; ++p) {
-      const float* b = pa.buf[pa.rank] + slot0 + static_cast<size_t>(p) * pa.slot_floats;
-      Moments m;
-      m.mean = ld_relaxed_sys(b + c);
-      m.m2 = ld_relaxed_sys(b + C + c);
-      m.n = ld_relaxed_sys(b + 2 * C + c);
-      r = merge(r, m);
-    }
-    const float var = r.n > 0.f ? r.m2 / r.n : 0.f;
-    const float invstd = rsqrtf(var + eps);
-    mean_invstd[c] = r.mean;
-    mean_invstd[C + c] = invstd;
-    const float sc = (gamma ? gamma[c] : 1.f) * invstd;
-    scale_shift[c] = sc;
-    scale_shift[C + c] = (beta ? beta[c] : 0.f) - r.mean * sc;
-    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * r.mean;
-    if (running_var) {
-      const float unb = r.n > 1.f ? r.m2 / (r.n - 1.f) : var;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
-    }
+  Moments r = {0.f, 0.f, 0.f};
+  for (int p = 0; p < pa.world; ++p) {
+    const unsigned long long* b = reinterpret_cast<const unsigned long long*>(pa.buf[pa.rank]) + slot0 +
+                                  static_cast<size_t>(p) * pa.slot_floats;
+    Moments m;
+    m.mean = ld_ll(b + c, seq, pa, p);
+    m.m2 = ld_ll(b + C + c, seq, pa, p);
+    m.n = ld_ll(b + 2 * C + c, seq, pa, p);
+    r = merge(r, m);
+  }
+  const float var = r.n > 0.f ? r.m2 / r.n : 0.f;
+  const float invstd = rsqrtf(var + eps);
+  mean_invstd[c] = r.mean;
+  mean_invstd[C + c] = invstd;
+  mean_invstd[2 * C + c] = r.n;     // samples per channel over all ranks (the backward's 1/count)
+  const float sc = (gamma ? gamma[c] : 1.f) * invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = (beta ? beta[c] : 0.f) - r.mean * sc;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * r.mean;
+  if (running_var) {
+    const float unb = r.n > 1.f ? r.m2 / (r.n - 1.f) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
   }
 }
 
@@ -864,21 +850,19 @@ __global__ void __launch_bounds__(1024) bn_bwd_reduce_final_p2p_kernel(const flo
   }
   sm[tl][cl] = acc;
   __syncthreads();
+  if (!(tl == 0 && idx < 2 * C)) return;
+  float own = 0.f;
+  for (int i = 0; i < 32; ++i) own += sm[i][cl];
+  sums_local[idx] = own;
+  const unsigned seq = pa.seq_ptr ? *pa.seq_ptr : pa.seq;
   const size_t slot0 = static_cast<size_t>(pa.slot) * pa.world * pa.slot_floats;
-  if (tl == 0 && idx < 2 * C) {
-    float r = 0.f;
-    for (int i = 0; i < 32; ++i) r += sm[i][cl];
-    sums_local[idx] = r;
-    const size_t off = slot0 + static_cast<size_t>(pa.rank) * pa.slot_floats + idx;
-    for (int p = 0; p < pa.world; ++p) pa.buf[p][off] = r;      // push to every peer (and to myself)
-  }
-  if (!peer_publish_and_wait(pa)) return;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {   // last block: all ranks' blocks are local -> totals, rank order
-    float r = 0.f;
-    for (int p = 0; p < pa.world; ++p)
-      r += ld_relaxed_sys(pa.buf[pa.rank] + slot0 + static_cast<size_t>(p) * pa.slot_floats + i);
-    sums_total[i] = r;
-  }
+  const size_t off = slot0 + static_cast<size_t>(pa.rank) * pa.slot_floats + idx;
+  for (int p = 0; p < pa.world; ++p) st_ll(reinterpret_cast<unsigned long long*>(pa.buf[p]) + off, own, seq);
+  float r = 0.f;
+  for (int p = 0; p < pa.world; ++p)
+    r += ld_ll(reinterpret_cast<const unsigned long long*>(pa.buf[pa.rank]) + slot0 + static_cast<size_t>(p) * pa.slot_floats + idx,
+               seq, pa, p);
+  sums_total[idx] = r;
 }
 
 static int ew_grid(long long total, int threads) {
@@ -1046,7 +1030,7 @@ extern "C" int semseg_bn_bwd_apply(const void* dy, const void* dy_lo, int dy_pit
                                    int dx_pitch, void* dres, void* dres_lo, int dres_pitch, float* dgamma_dbeta,
                                    void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SB_CHECK_ARG(dy && x && mean_invstd && sums && dx && M > 0 && C > 0 && count > 0.f, "bn_bwd_apply: bad args");
+  SB_CHECK_ARG(dy && x && mean_invstd && sums && dx && M > 0 && C > 0, "bn_bwd_apply: bad args");
   SB_CHECK_ARG(!relu || y || scale_shift, "bn_bwd_apply: relu needs y or scale_shift");
   SB_CHECK_ARG(C % 8 == 0 && dy_pitch % 8 == 0 && x_pitch % 8 == 0 && dx_pitch % 8 == 0 &&
                    (!(relu && y) || y_pitch % 8 == 0) && (!dres || dres_pitch % 8 == 0),
@@ -1061,7 +1045,7 @@ extern "C" int semseg_bn_bwd_apply(const void* dy, const void* dy_lo, int dy_pit
                              static_cast<const bf16*>(dy), static_cast<const bf16*>(dy_lo), dy_pitch,
                              static_cast<const bf16*>(y), static_cast<const bf16*>(y_lo), y_pitch,
                              static_cast<const bf16*>(x), static_cast<const bf16*>(x_lo), x_pitch, mean_invstd, gamma,
-                             scale_shift, sums, 1.f / count, M, C, relu, static_cast<bf16*>(dx),
+                             scale_shift, sums, count > 0.f ? 1.f / count : 0.f, M, C, relu, static_cast<bf16*>(dx),
                              static_cast<bf16*>(dx_lo), dx_pitch, static_cast<bf16*>(dres),
                              static_cast<bf16*>(dres_lo), dres_pitch, dgamma_dbeta));
   SB_LAUNCHED();

@@ -144,7 +144,9 @@ def _bn_backward(ctx_pg, world, dy, y, raw, mi, gamma, relu, want_dres, ss=None)
         if ctx_pg is not None:
             dbeta, dgamma = dbeta.clone(), dgamma.clone()  # local sums feed dgamma/dbeta (DDP averages them)
             dist.all_reduce(sums, group=ctx_pg)
-    count = float(n * h * w * world)
+    # under SyncBN the per-channel sample count is the one the forward exchange measured (mi row 2): exact also when the
+    # ranks hold different numbers of pixels, like torch.nn.SyncBatchNorm's gathered counts
+    count = float(n * h * w) if world == 1 else 0.0
     d_raw, dres, _ = ops.bn_bwd_apply(dy, y if relu else None, raw, mi, gamma, sums, count, relu, want_dres=want_dres,
                                       scale_shift=ss if y is None else None)
     return d_raw, dres, dgamma, dbeta

@@ -485,7 +485,7 @@ def bn_finalize(rank_stats, gamma, beta, eps, momentum, running_mean, running_va
         rank_stats = rank_stats.unsqueeze(0)
     r, _, c = rank_stats.shape
     assert rank_stats.is_contiguous()
-    mi = torch.empty((2, c), dtype=torch.float32, device=rank_stats.device)
+    mi = torch.empty((3, c), dtype=torch.float32, device=rank_stats.device)      # mean, invstd, total count
     ss = torch.empty((2, c), dtype=torch.float32, device=rank_stats.device)
     _lib.check(lib.semseg_bn_finalize(_ptr(rank_stats), r, c, _ptr(gamma), _ptr(beta), float(eps), float(momentum),
                                       _ptr(running_mean), _ptr(running_var), _ptr(mi), _ptr(ss), _stream()),
@@ -497,8 +497,8 @@ def bn_finalize_partials(stats_partial, gamma, beta, eps, momentum, running_mean
     """Per-tile conv partials -> (mean_invstd, scale_shift) in one launch (single-rank BatchNorm)."""
     lib = _lib.load()
     t, _, c = stats_partial.shape
-    buf = torch.empty((4, c), dtype=torch.float32, device=stats_partial.device)
-    mi, ss = buf[:2], buf[2:]
+    buf = torch.empty((5, c), dtype=torch.float32, device=stats_partial.device)
+    mi, ss = buf[:3], buf[3:]                               # (mean, invstd, total count), (scale, shift)
     _lib.check(lib.semseg_bn_finalize_partials(_ptr(stats_partial), t, c, _ptr(gamma), _ptr(beta),
                                                float(eps), float(momentum), _ptr(running_mean), _ptr(running_var),
                                                _ptr(mi), _ptr(ss), _stream()), "semseg_bn_finalize_partials")
@@ -764,8 +764,8 @@ def bn_finalize_p2p(stats_partial, gamma, beta, eps, momentum, running_mean, run
     """Like bn_finalize_partials, with the cross-rank exchange done inside the kernel over peer memory (px)."""
     lib = _lib.load()
     t, _, c = stats_partial.shape
-    buf = torch.empty((4, c), dtype=torch.float32, device=stats_partial.device)
-    mi, ss = buf[:2], buf[2:]
+    buf = torch.empty((5, c), dtype=torch.float32, device=stats_partial.device)
+    mi, ss = buf[:3], buf[3:]
     slot, seq = px.next()
     _lib.check(lib.semseg_bn_finalize_p2p(_ptr(stats_partial), t, c, _ptr(gamma), _ptr(beta), float(eps),
                                           float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(mi), _ptr(ss),

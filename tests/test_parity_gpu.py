@@ -232,7 +232,7 @@ def test_peer_exchange_kernels_world_of_one():
         def __init__(self):
             self.world, self.rank, self.calls = 1, 0, 0
             flag_words = p2p.N_SLOTS
-            self.buf = torch.zeros(flag_words + p2p.N_SLOTS * self.world * p2p.SLOT_FLOATS, device="cuda")
+            self.buf = torch.zeros(flag_words + 2 * p2p.N_SLOTS * self.world * p2p.SLOT_FLOATS, device="cuda")
             self.flag_ptrs = (ctypes.c_void_p * 1)(self.buf.data_ptr())
             self.data_ptrs = (ctypes.c_void_p * 1)(self.buf.data_ptr() + 4 * flag_words)
             self.counter = torch.zeros((1,), dtype=torch.int32, device="cuda")
