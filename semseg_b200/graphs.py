@@ -28,6 +28,7 @@ import torch.distributed as dist
 from . import precision
 
 WARMUP_CALLS = 3          # eager calls with an unchanged key before capturing
+MAX_GRAPHS = 4            # captured input shapes per model (each keeps a private activation pool); others stay eager
 _capturing = False
 _boundary = None          # activation noted by the model during capture: where the backward is cut in two
 
@@ -73,8 +74,25 @@ def _set_grad_outputs(st, g_main, g_aux):
         st.g_aux.copy_(g_aux)
 
 
-def _detached(gs):
-    return tuple(g.detach() if g is not None else None for g in gs)
+def _fresh(gs):
+    """Per-step copies of the graph's static gradient tensors, as views of ONE new flat buffer filled by a fused
+    multi-tensor copy: autograd's AccumulateGrad adopts such a view as `param.grad` without cloning it (it would clone
+    the static tensors themselves, one small kernel per parameter, because this module keeps references to them)."""
+    idx = [i for i, g in enumerate(gs) if g is not None]
+    if not idx:
+        return tuple(gs)
+    src = [gs[i] for i in idx]
+    offs, total = [], 0
+    for g in src:
+        offs.append(total)
+        total += (g.numel() + 3) & ~3                      # 16-byte aligned sub-buffers
+    flat = torch.empty((total,), dtype=src[0].dtype, device=src[0].device)
+    views = [flat[o:o + g.numel()].view(g.shape) for o, g in zip(offs, src)]
+    torch._foreach_copy_(views, src)
+    out = [None] * len(gs)
+    for i, v in zip(idx, views):
+        out[i] = v
+    return tuple(out)
 
 
 class _Replay(torch.autograd.Function):
@@ -96,7 +114,7 @@ class _Replay(torch.autograd.Function):
         st = ctx.st
         _set_grad_outputs(st, g_main, g_aux)
         st.bwd.replay()
-        return (None, None, None) + _detached(st.grads)
+        return (None, None, None) + _fresh(st.grads)
 
 
 class _ReplayHead(torch.autograd.Function):
@@ -117,7 +135,7 @@ class _ReplayHead(torch.autograd.Function):
         if d_mid.data_ptr() != st.d_mid.data_ptr():
             st.d_mid.copy_(d_mid)
         st.bwd2.replay()
-        return (None, None, None) + _detached(st.grads2)
+        return (None, None, None) + _fresh(st.grads2)
 
 
 class _ReplayTail(torch.autograd.Function):
@@ -136,7 +154,7 @@ class _ReplayTail(torch.autograd.Function):
         st = ctx.st
         _set_grad_outputs(st, g_main, g_aux)
         st.bwd.replay()
-        return (None, st.d_mid) + _detached(st.grads)
+        return (None, st.d_mid) + _fresh(st.grads)
 
 
 def _sync_bn_ready(model):
@@ -227,6 +245,8 @@ def train_step(model, impl, x, y):
     graphs when possible; returns None when the caller should run the eager path itself."""
     if not (enabled() and x.is_cuda and y is not None and torch.is_grad_enabled()):
         return None
+    if getattr(model, "_is_replica", False):
+        return None                           # nn.DataParallel replica (tool/train.py:159): rebuilt every call, threads
     steps = model.__dict__.setdefault("_sb_graph_steps", {})
     nparams = sum(1 for p in model.parameters() if p.requires_grad)
     key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, x.device.index, precision.get_mode(), nparams,
@@ -240,8 +260,8 @@ def train_step(model, impl, x, y):
         st.calls += 1
         if st.calls <= WARMUP_CALLS:
             return None                       # eager warm-up (also creates the weight-pack plan, the peer exchange, ...)
-        if not _sync_bn_ready(model):
-            st.failed = True
+        if not _sync_bn_ready(model) or sum(1 for v in steps.values() if v.fwd is not None) >= MAX_GRAPHS:
+            st.failed = True                  # NCCL-path SyncBN, or too many input shapes already hold a memory pool
             return None
         try:
             _capture(model, impl, st, x, y)
