@@ -382,6 +382,8 @@ def run_b200_arm(args):
                 # `ncu --set full` capture of the final build (profiles/r1_ncu_full_final_key_metrics.csv, first row):
                 # 738.1 MB + 72.5 MB per launch; the algorithmic bytes are 510 MB in + 59 MB out.
                 "traffic": 810.6e6 if (args.batch, fmap) == (16, 60) else None, "traffic_unit": "bytes/launch",
+                "traffic_source": "ncu --set full capture of round 1 (profiles/r1_ncu_full_final_key_metrics.csv); the "
+                                  "bf16 instantiation of this kernel and its tiling are unchanged in round 2",
                 "ms_per_launch": t_k, "peak_source": pk["source"] +
                 " burst bf16 (kernel timed alone)"}
         del xa, w, pw, flush
