@@ -723,10 +723,9 @@ __global__ void act_to_f32_kernel(const __nv_bfloat16* __restrict__ in, const __
 }
 
 // ------------------------------------------------------------------------------------------------
-// SyncBatchNorm statistics exchange over NVLink peer memory (torch symmetric memory): every rank publishes its
-// per-channel block in its own peer-mapped buffer, raises a flag in every peer's flag array, waits for the peers'
-// flags and then reads their blocks directly over NVLink. One kernel per exchange, no NCCL call, no stream hop;
-// the cross-rank merge is done in rank order on every rank, so all ranks compute bit-identical statistics.
+// SyncBatchNorm statistics exchange over NVLink peer memory (torch symmetric memory): one kernel per exchange, no NCCL
+// call, no stream hop; the protocol is described at st_ll / ld_ll below. The cross-rank merge is done in rank order on
+// every rank, so all ranks compute bit-identical statistics.
 struct PeerArgs {
   float* buf[8];        // peer-mapped data buffers (buf[rank] is local): 8-byte {value, seq} words, [slot][src rank][slot_floats]
   unsigned* flags[8];   // (unused by the LL protocol; kept in the ABI)
@@ -737,20 +736,6 @@ struct PeerArgs {
                             // into the graph, the sequence number is read at run time)
   long long timeout_ticks;
 };
-
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // Exchange protocol ("LL", flag-in-data): a value travels as ONE 8-byte word {fp32 bits, sequence number}. The sender
 // stores the word straight into sub-block `rank` of the slot in EVERY peer's buffer (posted NVLink stores); the receiver
