@@ -39,12 +39,10 @@ class FusedSGD(torch.optim.Optimizer):
             it.group, it.chunk0, it.first = gi, c0, int(first)
             c0 += (p.numel() + chunk - 1) // chunk
         dev = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(device)
-        host_ptrs = torch.zeros((len(plist),), dtype=torch.int64).pin_memory()
         dev_ptrs = torch.zeros((len(plist),), dtype=torch.int64, device=device)
         key = tuple((p.data_ptr(), self.state[p]["momentum_buffer"].data_ptr()) for _, p in plist)
         any_first = any(items[k].first for k in range(len(plist)))
-        return dict(items=dev, n=len(plist), chunks=c0, host_ptrs=host_ptrs, dev_ptrs=dev_ptrs, key=key,
-                    any_first=any_first)
+        return dict(items=dev, n=len(plist), chunks=c0, dev_ptrs=dev_ptrs, last_ptrs=None, key=key, any_first=any_first)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -63,13 +61,18 @@ class FusedSGD(torch.optim.Optimizer):
                      if self.state[p].get("momentum_buffer") is not None else 0) for _, p in plist)
         if t is None or t["key"] != key or t["any_first"]:
             t = self._table = self._build(plist, plist[0][1].device)
-        hp = t["host_ptrs"]
-        for k, (_, p) in enumerate(plist):
+        ptrs = []
+        for _, p in plist:
             g = p.grad
             if g is not None and not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous()):
                 g = p.grad = g.contiguous().float()
-            hp[k] = g.data_ptr() if g is not None else 0
-        t["dev_ptrs"].copy_(hp, non_blocking=True)
+            ptrs.append(g.data_ptr() if g is not None else 0)
+        if ptrs != t["last_ptrs"]:
+            # Upload the gradient pointer table only when it changed, from a FRESH pinned buffer each time: the copy is
+            # asynchronous, so a reused staging buffer could be overwritten by the next step's pointers before this
+            # step's copy has run (torch's pinned-memory allocator keeps a freed block alive until its copy completed).
+            t["dev_ptrs"].copy_(torch.tensor(ptrs, dtype=torch.int64).pin_memory(), non_blocking=True)
+            t["last_ptrs"] = ptrs
         h = _lib.SgdHyper()
         for gi, g in enumerate(self.param_groups):
             h.lr[gi], h.momentum[gi] = float(g["lr"]), float(g["momentum"])
