@@ -12,7 +12,7 @@ into two CUDA graphs (the same kernels, in the same order, on the same stream) a
 whose inputs are the module's parameters: `loss.backward()`, DDP's gradient hooks, `optimizer.step()` and checkpoints see
 exactly what they saw before. Captured along with the kernels: the one-launch weight re-pack, the BatchNorm
 running-statistics updates, the SyncBN peer exchanges (their slots are baked in, the sequence number is a device-resident
-step counter incremented inside the graph — csrc/bn.cu peer_publish_and_wait) and dropout's Philox state.
+step counter incremented inside the graph — csrc/bn.cu st_ll / ld_ll) and dropout's Philox state.
 
 Limits (same as torch.cuda.make_graphed_callables): a second training forward before the backward of the first one
 overwrites the first one's saved activations — gradient accumulation over several forwards needs SEMSEG_B200_GRAPH=0.
@@ -248,8 +248,10 @@ def train_step(model, impl, x, y):
     if getattr(model, "_is_replica", False):
         return None                           # nn.DataParallel replica (tool/train.py:159): rebuilt every call, threads
     steps = model.__dict__.setdefault("_sb_graph_steps", {})
-    nparams = sum(1 for p in model.parameters() if p.requires_grad)
-    key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, x.device.index, precision.get_mode(), nparams,
+    # the graphs address the parameters' storage directly: a parameter that was re-allocated since the capture
+    # (model.to(...), a swapped nn.Parameter) must not hit a stale graph, so the storage addresses are part of the key
+    ptrs = tuple(p.data_ptr() for p in model.parameters() if p.requires_grad)
+    key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, x.device.index, precision.get_mode(), len(ptrs), hash(ptrs),
            dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1)
     st = steps.get(key)
     if st is None:
