@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stock-gpu", action="store_true")
     ap.add_argument("--no-parity-mode", action="store_true")
+    ap.add_argument("--parity-mode-multi", action="store_true", help="also time the bf16x3 leg when --gpus > 1")
     ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
                     help="torch.optim.SGD (the reference's, tool/train.py:140) or semseg_b200.optim.FusedSGD (one launch)")
     return ap.parse_args()
@@ -335,7 +336,9 @@ def run_b200_arm(args):
     # ---- the same step in the parity-precision operand mode (bf16x3: hi/lo bf16 pairs, three MMA segments per K block;
     #      the mode whose eval logits match the fp32 reference to 1e-3 with identical argmax, tests/test_parity_x3_gpu.py)
     parity = None
-    if not args.no_parity_mode:
+    if not args.no_parity_mode and (world == 1 or args.parity_mode_multi):
+        # N > 1: off by default — the scaling runs measure the speed configuration only; the parity mode's multi-rank
+        # correctness is covered by tests/test_multigpu_gpu.py, its throughput by the N = 1 line
         from semseg_b200 import precision
         psteps = max(1, min(args.steps, 5))
         try:
