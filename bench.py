@@ -152,6 +152,12 @@ def run_reference_modules(args, device, batch, steps, warmup, threads=0, timeout
     env["PYTHONPATH"] = REF_DIR
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
         env.pop(k, None)
+    if device == "cuda":
+        # nn.DataParallel (tool/train.py:159) spreads over every visible GPU: pin the runner to the ONE GPU this bench
+        # process measures on, so that "same GPU, same workload" holds on a multi-GPU box too
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        lr = int(os.environ.get("LOCAL_RANK", "0"))
+        env["CUDA_VISIBLE_DEVICES"] = vis[lr] if lr < len(vis) else str(lr)
     cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_reference.py"), "--device", device, "--arch", args.arch,
            "--layers", str(args.layers), "--classes", str(args.classes), "--size", str(args.size), "--batch",
            str(batch), "--steps", str(steps), "--warmup", str(warmup), "--threads", str(threads)]
