@@ -111,3 +111,38 @@ def test_product_package_never_imports_oracle():
                 if f.endswith(".py"):
                     src = open(os.path.join(dirpath, f)).read()
                     assert "import oracle" not in src and "from oracle" not in src, os.path.join(dirpath, f)
+
+
+def test_bench_reference_runner_environment(monkeypatch):
+    """bench.py's reference-module runner (baseline/run_reference.py) starts with the reference tree ALONE on PYTHONPATH,
+    without the torchrun rendezvous variables, and — for the GPU leg — pinned to the one GPU the bench process measures on
+    (nn.DataParallel, tool/train.py:159, would otherwise spread over every visible GPU of a multi-GPU box)."""
+    import argparse
+    import subprocess
+    import bench
+    seen = {}
+
+    class Done:
+        returncode, stdout, stderr = 0, 'noise\n{"images_per_sec": 1.0}\n', ""
+
+    def fake_run(cmd, cwd=None, env=None, **kw):
+        seen.update(cmd=cmd, cwd=cwd, env=env)
+        return Done()
+
+    monkeypatch.setattr(subprocess, "run", fake_run)
+    args = argparse.Namespace(arch="psp", layers=50, classes=150, size=473)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "3,5")
+    monkeypatch.setenv("LOCAL_RANK", "1")
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    assert bench.run_reference_modules(args, "cuda", 16, 5, 3) == {"images_per_sec": 1.0}
+    assert seen["env"]["CUDA_VISIBLE_DEVICES"] == "5"
+    assert seen["env"]["PYTHONPATH"] == bench.REF_DIR and seen["cwd"] == bench.REF_DIR
+    assert not any(k in seen["env"] for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"))
+    assert seen["cmd"][1].endswith("baseline/run_reference.py") and "--device" in seen["cmd"]
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    bench.run_reference_modules(args, "cuda", 16, 5, 3)
+    assert seen["env"]["CUDA_VISIBLE_DEVICES"] == "0"
+    bench.run_reference_modules(args, "cpu", 2, 2, 1, threads=8)
+    assert "CUDA_VISIBLE_DEVICES" not in seen["env"] and seen["cmd"][seen["cmd"].index("--threads") + 1] == "8"
