@@ -146,3 +146,34 @@ def test_bench_reference_runner_environment(monkeypatch):
     assert seen["env"]["CUDA_VISIBLE_DEVICES"] == "0"
     bench.run_reference_modules(args, "cpu", 2, 2, 1, threads=8)
     assert "CUDA_VISIBLE_DEVICES" not in seen["env"] and seen["cmd"][seen["cmd"].index("--threads") + 1] == "8"
+
+
+def test_precision_mode_switch_and_graph_gates(monkeypatch):
+    """Host-side switches: the operand policy (semseg_b200/precision.py) and the CUDA-graph gate (graphs.enabled /
+    train_step declining anything that is not a CUDA training call)."""
+    from semseg_b200 import graphs, precision
+    assert precision.get_mode() in precision.MODES
+    before = precision.get_mode()
+    with precision.mode("bf16x3"):
+        assert precision.split_enabled() and precision.get_mode() == "bf16x3"
+        with precision.mode("bf16"):
+            assert not precision.split_enabled()
+        assert precision.split_enabled()
+    assert precision.get_mode() == before
+    with pytest.raises(ValueError):
+        precision.set_mode("fp8")
+    with pytest.raises(ValueError):
+        with precision.mode("tf32"):
+            pass
+    assert precision.get_mode() == before
+    monkeypatch.setenv("SEMSEG_B200_GRAPH", "0")
+    assert not graphs.enabled()
+    monkeypatch.delenv("SEMSEG_B200_GRAPH")
+    assert graphs.enabled() and not graphs.capturing()
+    # a CPU call, a call without target and a call under no_grad are never captured: the caller runs its eager path
+    x, y = torch.zeros((1, 3, 9, 9)), torch.zeros((1, 9, 9), dtype=torch.long)
+    m = torch.nn.Conv2d(3, 3, 1)
+    assert graphs.train_step(m, None, x, y) is None
+    assert graphs.launches_per_step(m) == 0
+    t = torch.ones(3, requires_grad=True)
+    assert graphs.note_boundary(t) is t           # outside a capture: identity, nothing recorded
