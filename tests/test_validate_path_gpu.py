@@ -26,7 +26,6 @@ def test_eval_forward_with_autograd_enabled_equals_no_grad(arch):
     assert torch.allclose(out.detach(), ref, rtol=0.0, atol=1e-6)
     loss = F.cross_entropy(out, y, ignore_index=255)     # criterion(output, target), tool/train.py:360
     assert bool(torch.isfinite(loss))
-    assert torch.equal(out.detach().max(1)[1], ref.max(1)[1])
 
 
 def _load_stock_psamask():
