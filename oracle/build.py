@@ -5,6 +5,9 @@
                   /root/reference (nothing is copied) into oracle/_ref/psamask_ref_cpu.so with
                   torch.utils.cpp_extension (the files include <torch/torch.h>, so torch's headers are needed;
                   no other external dependency, no build system of the reference is run).
+  build_ref_gpu(): likewise lib/psa/src/gpu/{operator.cpp,psamask_cuda.cu} -> oracle/_ref/psamask_ref_gpu.so (nvcc
+                  cross-compiles for sm_100 without a GPU): the checker of tests/test_validate_path_gpu.py and the
+                  baseline of tools/bench_psamask.py.
 """
 import os
 import subprocess
@@ -46,7 +49,8 @@ def build_ref(verbose=False):
 def build_ref_gpu(verbose=False):
     """The reference's own CUDA extension (lib/psa/src/gpu/{operator.cpp,psamask_cuda.cu} — "the kernel the rewrite must
     beat") cross-compiled for sm_100 where the sources lie, into oracle/_ref/psamask_ref_gpu*.so. Used
-    only by tools/bench_psamask.py (a same-box timing of stock vs rewritten kernel). None when /root/reference is absent."""
+    by tools/bench_psamask.py (a same-box timing of stock vs rewritten kernel) and tests/test_validate_path_gpu.py (bit
+    equality). None when /root/reference is absent."""
     gpu_dir = os.path.join(REFERENCE, "lib", "psa", "src", "gpu")
     ref_dir = os.path.join(HERE, "_ref")
 
