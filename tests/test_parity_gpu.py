@@ -467,6 +467,9 @@ def test_bottleneck_block_vs_oracle(dil, planes):
     # flipped element is an O(1) change of dz, i.e. a relative L2 error of ~sqrt(0.003) = 5 % that no kernel can
     # avoid (the backward kernels themselves are checked to 3e-3 in the kernel-level tests above). A wrong
     # kernel or a missing gradient branch shows up as an error of order 1 and a low cosine similarity.
+    # The TIGHT gradient gate of this block lives in tests/test_parity_x3_gpu.py::test_bottleneck_block_x3_vs_oracle: the
+    # same kernels (one template, two storage forms) in the bf16x3 mode, <= 1e-3 against the fp32 reference evaluated
+    # with the same ReLU masks — a dropped or mis-scaled gradient term cannot pass there.
     def cos(a, b):
         a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
         return float((a * b).sum() / (a.norm() * b.norm()))
